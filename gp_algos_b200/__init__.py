@@ -1,0 +1,20 @@
+"""gp_algos_b200 -- B200-native (sm_100a) drop-in for the dense-GP hot path of astroHaoPeng/gp_algos.
+
+The numeric work lives in ``libgpk.so`` (hand-written CUDA, C ABI in include/gpk.h).  This package is
+the host-side mirror of the reference's Scala interface for that path (same names, argument meaning
+and error behaviour), used by the parity tests and the benchmark:
+
+    utils.KernelRequisites  ->  gp_algos_b200.kernel_requisites  (GaussianRbfParams, GaussianRbfKernel)
+    utils.MatrixUtils       ->  gp_algos_b200.matrix_utils       (buildKernelMatrix, forwardSolve, ...)
+    gp.regression.GpPredictor -> gp_algos_b200.gp_predictor      (GpPredictor, PredictionInput, ...)
+
+There is no CPU fallback: importing works anywhere, but every numeric call raises if libgpk.so or a
+CUDA device is missing.
+"""
+from .kernel_requisites import GaussianRbfKernel, GaussianRbfParams  # noqa: F401
+from .gp_predictor import GpPredictor, PredictionInput, PredictionTrainingInput, GaussianDistribution  # noqa: F401
+from . import matrix_utils as MatrixUtils  # noqa: F401
+from ._lib import GpkError, NotPositiveDefiniteError, MatrixNotSymmetricError, lib_path  # noqa: F401
+
+__all__ = ["GaussianRbfKernel", "GaussianRbfParams", "GpPredictor", "PredictionInput", "PredictionTrainingInput",
+           "GaussianDistribution", "MatrixUtils", "GpkError", "NotPositiveDefiniteError", "MatrixNotSymmetricError"]

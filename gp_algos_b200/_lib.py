@@ -1,0 +1,155 @@
+"""ctypes binding of libgpk.so (include/gpk.h).  Fails loudly when the library or a GPU is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_i64 = C.c_int64
+
+GPK_OK, GPK_EINVAL, GPK_ENOTSYM, GPK_ENOTPD, GPK_ECUDA, GPK_ENOMEM = 0, -1, -2, -3, -4, -5
+
+
+class GpkError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"libgpk status {status}: {msg}")
+        self.status = status
+
+
+class IllegalArgumentError(GpkError, ValueError):
+    """java.lang.IllegalArgumentException (`require` at GpPredictor.scala:108, MatrixUtils.scala:125)."""
+
+
+class MatrixNotSymmetricError(GpkError):
+    """breeze.linalg.MatrixNotSymmetricException."""
+
+
+class NotPositiveDefiniteError(GpkError):
+    """breeze.linalg.NotConvergedException raised by `cholesky`; .minor = failing leading minor (1-based)."""
+
+    def __init__(self, status, msg, minor):
+        super().__init__(status, msg)
+        self.minor = minor
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libgpk.so")
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libgpk.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path):
+            raise GpkError(GPK_ECUDA, f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                      f"(there is no CPU fallback)")
+        lib = C.CDLL(path)
+        lib.gpk_version.restype = C.c_char_p
+        lib.gpk_last_error.restype = C.c_char_p
+        lib.gpk_last_error.argtypes = [C.c_void_p]
+        lib.gpk_last_info.argtypes = [C.c_void_p]
+        lib.gpk_launch_count.restype = C.c_int64
+        lib.gpk_launch_count.argtypes = [C.c_void_p]
+        lib.gpk_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+        lib.gpk_destroy.argtypes = [C.c_void_p]
+        lib.gpk_synchronize.argtypes = [C.c_void_p]
+        vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+        lib.gpk_cov_se_ard.argtypes = [vp, vp, ci, ci, _i64, vp, vp, _i64]
+        lib.gpk_cov_se_ard_dev.argtypes = [vp, vp, ci, ci, _i64, vp, vp, _i64]
+        lib.gpk_cov_cross_se_ard.argtypes = [vp, vp, ci, _i64, vp, ci, _i64, ci, vp, vp, _i64]
+        lib.gpk_cov_cross_se_ard_dev.argtypes = [vp, vp, ci, _i64, vp, ci, _i64, ci, vp, vp, _i64]
+        lib.gpk_cov_deriv_se_ard.argtypes = [vp, ci, vp, ci, ci, _i64, vp, vp, _i64]
+        lib.gpk_potrf_lower.argtypes = [vp, vp, ci, _i64, vp, _i64, ci]
+        lib.gpk_trsm.argtypes = [vp, ci, ci, vp, ci, _i64, vp, ci, _i64, vp, _i64]
+        lib.gpk_trtri.argtypes = [vp, ci, vp, ci, _i64, vp, _i64]
+        lib.gpk_gp_fit.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, cd, vp, _i64, vp, vp]
+        lib.gpk_gp_nll_grad.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, cd, ci, vp, vp]
+        lib.gpk_gp_nll_grad_dev.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, cd, ci, vp, vp]
+        lib.gpk_gp_model_fit.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, cd, C.POINTER(vp), vp]
+        lib.gpk_gp_model_from_factor.argtypes = [vp, vp, ci, ci, _i64, vp, _i64, vp, vp, C.POINTER(vp)]
+        lib.gpk_gp_model_destroy.argtypes = [vp, vp]
+        lib.gpk_gp_model_predict.argtypes = [vp, vp, vp, ci, _i64, ci, vp, vp, _i64, vp, _i64]
+        lib.gpk_gp_predict.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, _i64, vp, ci, cd, vp, vp, _i64, vp]
+        _lib = lib
+        return lib
+
+
+class Handle:
+    """One libgpk handle = one device + one stream (include/gpk.h). Not re-entrant."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load()
+        self._h = C.c_void_p()
+        rc = self.lib.gpk_create(C.byref(self._h), int(device), C.c_void_p(stream) if stream else None)
+        if rc != GPK_OK:
+            raise GpkError(rc, f"gpk_create(device={device}) failed: no usable CUDA device "
+                               f"(libgpk has no CPU fallback)")
+        self.device = device
+
+    @property
+    def h(self):
+        return self._h
+
+    def check(self, rc):
+        if rc == GPK_OK:
+            return
+        msg = self.lib.gpk_last_error(self._h).decode()
+        if rc == GPK_EINVAL:
+            raise IllegalArgumentError(rc, msg)
+        if rc == GPK_ENOTSYM:
+            raise MatrixNotSymmetricError(rc, msg)
+        if rc == GPK_ENOTPD:
+            raise NotPositiveDefiniteError(rc, msg, self.lib.gpk_last_info(self._h))
+        raise GpkError(rc, msg)
+
+    def launch_count(self) -> int:
+        return int(self.lib.gpk_launch_count(self._h))
+
+    def synchronize(self):
+        self.check(self.lib.gpk_synchronize(self._h))
+
+    def close(self):
+        if self._h:
+            self.lib.gpk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default = {}
+
+
+def default_handle(device: int = 0) -> Handle:
+    """Process-wide handle per device (the Scala objects are singletons too, spring-context.xml)."""
+    if device not in _default:
+        _default[device] = Handle(device)
+    return _default[device]
+
+
+def fmat(a) -> np.ndarray:
+    """Column-major float64 view/copy: the Breeze DenseMatrix layout expected by the ABI."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 2 and not a.flags.f_contiguous:
+        a = np.asfortranarray(a)
+    elif a.ndim == 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,182 @@
+// gpk_gemm.cu -- FP64 tensor-core (DMMA.8x8x4) tile GEMM used by every O(n^3) step of the path:
+// Cholesky trailing update (SYRK), L21 = A21 L11^-T, the blocked triangular inverse, K^-1 = L^-T L^-1
+// (reference: GpPredictor.scala:66-67,120; EpParameterEstimator.scala:58-60) and the predictive
+// V = L^-1 K*^t (GpPredictor.scala:34,55).
+//
+// sm_100a has no tcgen05 kind for f64 (ptxas rejects .kind::f64), so the FP64 tensor path is the
+// warp-level mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4.  Measured on B200 (profiles/r01_fp64_microbench.txt):
+// DMMA and DFMA both peak at 37.1 TFLOP/s; DMMA needs 4x fewer shared-memory operand bytes per flop,
+// which is what lets a 128x128x16 CTA tile with 64x32 warp tiles run pipe-bound.
+//
+// Layout: 256 threads = 8 warps as 2 (r) x 4 (s); each warp owns a 64 x 32 sub-tile = 8 x 4 DMMA
+// accumulators (128 registers/thread).  Operands are staged global -> shared with 16-byte cp.async
+// (LDGSTS) through a 4-stage ring; shared rows are padded by 4 doubles so that the 8-byte fragment
+// reads of a half-warp (4 k x 4 rows) hit 16 distinct bank pairs.
+#include "gpk_internal.cuh"
+
+namespace {
+
+constexpr int TR = 128, TS = 128, TK = 16, STAGES = 4, NTHREADS = 256;
+constexpr int LDR = TR + 4;  // row stride (doubles) of a [k][x] stage   (x-contiguous source)
+constexpr int LDK = TK + 4;  // row stride (doubles) of a [x][k] stage   (k-contiguous source)
+constexpr int STAGE_DOUBLES = (TR * LDK > TK * LDR) ? TR * LDK : TK * LDR;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * 2 * STAGE_DOUBLES * sizeof(double);
+constexpr int GROUP_S = 8;  // raster: blocks walk bands of 8 s-tiles so a wave shares operand panels in L2
+
+__device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// stage a 128 (x) by 16 (k) operand tile
+template <bool KC>
+__device__ __forceinline__ void load_tile(double* st, const double* g, int64_t ld, int x0, int k0, int tid) {
+    if (!KC) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int c = tid + i * NTHREADS;
+            int k = c >> 6, x = (c & 63) * 2;
+            cp_async16(st + k * LDR + x, g + (int64_t)(k0 + k) * ld + (x0 + x));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int c = tid + i * NTHREADS;
+            int x = c >> 3, k = (c & 7) * 2;
+            cp_async16(st + x * LDK + k, g + (int64_t)(x0 + x) * ld + (k0 + k));
+        }
+    }
+}
+
+template <bool PK, bool QK>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_dmma_kernel(const GemmDesc g) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int tilesS = g.S / TS, tilesR = g.R / TR;
+    int bid = blockIdx.x;
+    if (g.heavy_last) bid = gridDim.x - 1 - bid;
+    const int group = bid / (GROUP_S * tilesR);
+    const int first_s = group * GROUP_S;
+    const int gs = min(GROUP_S, tilesS - first_s);
+    const int within = bid - group * GROUP_S * tilesR;
+    const int tr = within / gs, ts = first_s + within % gs;
+    if (g.tri_out && ts < tr) return;
+    const int r0 = tr * TR, s0 = ts * TS;
+    int kbeg = 0, kend = g.K;
+    if (g.kb_r) kbeg = max(kbeg, r0);
+    if (g.kb_s) kbeg = max(kbeg, s0);
+    if (g.ke_r) kend = min(kend, r0 + TR);
+    if (g.ke_s) kend = min(kend, s0 + TS);
+    const int nk = (kend - kbeg) / TK;
+
+    const int64_t b = blockIdx.y;
+    const double* __restrict__ P = g.P + b * g.strideP;
+    const double* __restrict__ Q = g.Q + b * g.strideQ;
+    double* __restrict__ D = g.D + b * g.strideD;
+    const double* Cin = g.Cin ? g.Cin + b * g.strideC : nullptr;
+
+    double* Ps = smem;
+    double* Qs = smem + STAGES * STAGE_DOUBLES;
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wr0 = (warp >> 2) * 64, ws0 = (warp & 3) * 32;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) {
+            load_tile<PK>(Ps + s * STAGE_DOUBLES, P, g.ldp, r0, kbeg + s * TK, tid);
+            load_tile<QK>(Qs + s * STAGE_DOUBLES, Q, g.ldq, s0, kbeg + s * TK, tid);
+        }
+        cp_async_commit();
+    }
+
+    for (int kc = 0; kc < nk; ++kc) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nx = kc + STAGES - 1;
+            if (nx < nk) {
+                const int st = nx % STAGES;
+                load_tile<PK>(Ps + st * STAGE_DOUBLES, P, g.ldp, r0, kbeg + nx * TK, tid);
+                load_tile<QK>(Qs + st * STAGE_DOUBLES, Q, g.ldq, s0, kbeg + nx * TK, tid);
+            }
+            cp_async_commit();
+        }
+        const double* ps = Ps + (kc % STAGES) * STAGE_DOUBLES;
+        const double* qs = Qs + (kc % STAGES) * STAGE_DOUBLES;
+        const double* pf = PK ? ps + (wr0 + gid) * LDK + tig : ps + tig * LDR + wr0 + gid;
+        const double* qf = QK ? qs + (ws0 + gid) * LDK + tig : qs + tig * LDR + ws0 + gid;
+#pragma unroll
+        for (int kk = 0; kk < TK; kk += 4) {
+            double a[8], bb[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = PK ? pf[i * 8 * LDK + kk] : pf[kk * LDR + i * 8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bb[j] = QK ? qf[j * 8 * LDK + kk] : qf[kk * LDR + j * 8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    const double alpha = g.alpha, beta = g.beta;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = r0 + wr0 + 8 * i + gid;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int s = s0 + ws0 + 8 * j + 2 * tig;
+            double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+            if (Cin != nullptr) {
+                const double2 c = *reinterpret_cast<const double2*>(Cin + r * g.ldc + s);
+                v.x += beta * c.x;
+                v.y += beta * c.y;
+            }
+            *reinterpret_cast<double2*>(D + r * g.ldd + s) = v;
+        }
+    }
+}
+
+template <bool PK, bool QK>
+int launch(gpk_handle h, const GemmDesc& g) {
+    const unsigned bit = 1u << ((PK ? 2 : 0) + (QK ? 1 : 0));
+    if (!(h->func_cfg & bit)) {
+        GPK_CUDA(h, cudaFuncSetAttribute(gemm_f64_dmma_kernel<PK, QK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM_BYTES));
+        h->func_cfg |= bit;
+    }
+    dim3 grid((unsigned)((g.R / TR) * (g.S / TS)), (unsigned)g.batch);
+    gemm_f64_dmma_kernel<PK, QK><<<grid, NTHREADS, SMEM_BYTES, h->stream>>>(g);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+}  // namespace
+
+int gpk_gemm(gpk_handle h, const GemmDesc& g) {
+    if (g.R <= 0 || g.S <= 0 || g.batch <= 0) return GPK_OK;
+    if (g.R % TR || g.S % TS || g.K % TK || (g.ldp & 1) || (g.ldq & 1) || (g.ldd & 1) ||
+        ((uintptr_t)g.P & 15) || ((uintptr_t)g.Q & 15) || ((uintptr_t)g.D & 15) || (g.Cin && (((uintptr_t)g.Cin & 15) || (g.ldc & 1))))
+        return gpk_set_error(h, GPK_EINVAL, "gpk_gemm: unaligned problem R=%d S=%d K=%d", g.R, g.S, g.K);
+    if (g.p_kcontig) return g.q_kcontig ? launch<true, true>(h, g) : launch<true, false>(h, g);
+    return g.q_kcontig ? launch<false, true>(h, g) : launch<false, false>(h, g);
+}

@@ -1,0 +1,189 @@
+// gpk_grad.cu -- fused likelihood-gradient trace.
+// Reference (GpPredictor.scala:69-78): for every hyper-parameter p it materialises dK/dtheta_p with one
+// closure call per element (MatrixUtils.scala:72-84 + KernelRequisites.scala:76-86), runs a full n x n x n dgemm
+// (alphaSq - inversedK) * dK_p and takes the trace: P * (2 n^3 flops + 8 n^2 bytes).
+// Here: g_p = 1/2 sum_ij W_ij dk_p(x_i,x_j,[i==j]),  W = alpha alpha^t - K^-1, in ONE pass over the lower
+// triangle of K^-1 (symmetry: off-diagonal terms counted twice).  dk_p is recomputed from X tiles staged in
+// shared memory, so dK/dtheta is never materialised: 4 n^2 bytes read, O(n^2 (D + 30)) FP64 flops.
+//   p = 1      : dk = 2 sf e                       e = exp(-r/2)
+//   2..D+1     : dk = sf^2 e (x_id - x_jd)^2 / l_d^3
+//   D+2        : dk = 2 sn [i == j]
+#include "gpk_internal.cuh"
+
+namespace {
+
+constexpr int GT = 64;  // tile edge
+constexpr int GC = 8;   // parameters accumulated per register chunk
+
+struct GradArgs {
+    const double* Kinv; int N;
+    const double* X; int64_t ldx; int n;
+    const double* alpha;
+    double* partial;  // [numBlocks][D + 2]
+    CovParams cp;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 8; ++i) s += red[i];
+    return s;  // valid on thread 0
+}
+
+__global__ void __launch_bounds__(256) grad_trace_kernel(const GradArgs a) {
+    extern __shared__ double sm[];  // xi[D][GT], xj[D][GT]
+    __shared__ double red[8];
+    const int D = a.cp.D;
+    double* xi = sm;
+    double* xj = sm + D * GT;
+    // linear block id -> lower-triangular tile (bi >= bj)
+    const int t = blockIdx.x;
+    int bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    while ((int64_t)bi * (bi + 1) / 2 > t) --bi;
+    const int bj = t - (int)((int64_t)bi * (bi + 1) / 2);
+    const int i0 = bi * GT, j0 = bj * GT;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+
+    for (int e = tid; e < D * GT; e += 256) {
+        const int d = e / GT, l = e % GT;
+        const int gi = i0 + l, gj = j0 + l;
+        xi[e] = (gi < a.n) ? a.X[gi + (int64_t)d * a.ldx] : 0.0;
+        xj[e] = (gj < a.n) ? a.X[gj + (int64_t)d * a.ldx] : 0.0;
+    }
+    __syncthreads();
+
+    // per-thread elements: rows gi0, gi0+1; columns j0 + ty + 8b
+    const int gi0 = i0 + 2 * tx;
+    double we[2][8];  // mult * W_ij * e_ij   (0 for masked elements)
+    double wdiag = 0.0;
+    {
+        double r[2][8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) r[q][b] = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double inv = a.cp.inv_ls2[d];
+            const double x0 = xi[d * GT + 2 * tx], x1 = xi[d * GT + 2 * tx + 1];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const double xv = xj[d * GT + ty + 8 * b];
+                const double f0 = x0 - xv, f1 = x1 - xv;
+                r[0][b] += (f0 * inv) * f0;
+                r[1][b] += (f1 * inv) * f1;
+            }
+        }
+        const double al0 = (gi0 < a.n) ? a.alpha[gi0] : 0.0, al1 = (gi0 + 1 < a.n) ? a.alpha[gi0 + 1] : 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int gj = j0 + ty + 8 * b;
+            const double aj = (gj < a.n) ? a.alpha[gj] : 0.0;
+            const double2 kv = *reinterpret_cast<const double2*>(a.Kinv + gi0 + (int64_t)gj * a.N);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int gi = gi0 + q;
+                const double w = (q ? al1 : al0) * aj - (q ? kv.y : kv.x);
+                const bool valid = gi < a.n && gj < a.n && gi >= gj;
+                const double mult = (gi == gj) ? 1.0 : 2.0;
+                we[q][b] = valid ? mult * w * exp(-0.5 * r[q][b]) : 0.0;
+                if (valid && gi == gj) wdiag += w;
+            }
+        }
+    }
+
+    double* out = a.partial + (int64_t)blockIdx.x * (D + 2);
+    {   // p = 1 (signal) and p = D+2 (noise)
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) s += we[q][b];
+        const double ts = block_sum(s, red);
+        const double tn = block_sum(wdiag, red);
+        if (tid == 0) { out[0] = ts; out[D + 1] = tn; }
+    }
+    for (int d0 = 0; d0 < D; d0 += GC) {
+        double acc[GC];
+#pragma unroll
+        for (int c = 0; c < GC; ++c) acc[c] = 0.0;
+#pragma unroll
+        for (int c = 0; c < GC; ++c) {
+            const int d = d0 + c;
+            if (d < D) {
+                const double x0 = xi[d * GT + 2 * tx], x1 = xi[d * GT + 2 * tx + 1];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const double xv = xj[d * GT + ty + 8 * b];
+                    const double f0 = x0 - xv, f1 = x1 - xv;
+                    acc[c] += we[0][b] * (f0 * f0) + we[1][b] * (f1 * f1);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < GC; ++c) {
+            if (d0 + c < D) {
+                const double tsum = block_sum(acc[c], red);
+                if (tid == 0) out[1 + d0 + c] = tsum;
+            }
+        }
+    }
+}
+
+// g[p] = scale[p] * sum_blocks partial[block][p]   (fixed order -> deterministic)
+struct GradScale { double s[GPK_MAX_D + 2]; };
+__global__ void __launch_bounds__(256) grad_finish_kernel(const double* partial, int nblocks, int np_all, int nparams,
+                                                          const GradScale scale, double* g) {
+    __shared__ double sd[256];
+    const int p = blockIdx.x;
+    if (p >= nparams) return;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(int64_t)b * np_all + p];
+    sd[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) sd[threadIdx.x] += sd[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) g[p] = scale.s[p] * sd[0];
+}
+
+}  // namespace
+
+size_t gpk_grad_scratch_doubles(int N, int D) {
+    const size_t tiles = (size_t)(N / GT) * (N / GT + 1) / 2;
+    return tiles * (D + 2) + (D + 2);
+}
+
+int gpk_grad_trace(gpk_handle h, const double* Kinv, int N, const double* dX, int n, int64_t ldx, const double* alpha,
+                   const CovParams& cp, double sf, double sn, const double* ls_host, int nparams, double* g_out,
+                   double* scratch) {
+    const int D = cp.D;
+    if (nparams < 0 || nparams > D + 2) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, D + 2);
+    if (nparams == 0) return GPK_OK;
+    const int nt = (n + GT - 1) / GT;
+    const int nblocks = nt * (nt + 1) / 2;
+    GradArgs a;
+    a.Kinv = Kinv; a.N = N; a.X = dX; a.ldx = ldx; a.n = n; a.alpha = alpha; a.partial = scratch; a.cp = cp;
+    const size_t smem = (size_t)2 * D * GT * sizeof(double);
+    if (smem > 48 * 1024 && !(h->func_cfg & (1u << 9))) {
+        GPK_CUDA(h, cudaFuncSetAttribute(grad_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->func_cfg |= (1u << 9);
+    }
+    grad_trace_kernel<<<nblocks, 256, smem, h->stream>>>(a);
+    GPK_LAUNCH_CHECK(h);
+    // scale factors: 1/2 * {2 sf, sf^2 / l_d^3, 2 sn}
+    GradScale sc;
+    sc.s[0] = sf;
+    for (int d = 0; d < D; ++d) sc.s[1 + d] = 0.5 * (sf * sf) / (ls_host[d] * ls_host[d] * ls_host[d]);
+    sc.s[D + 1] = sn;
+    grad_finish_kernel<<<nparams, 256, 0, h->stream>>>(scratch, nblocks, D + 2, nparams, sc, g_out);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}

@@ -1,0 +1,145 @@
+// gpk_internal.cuh -- shared declarations of libgpk's translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gpk.h"
+
+#define GPK_TILE 128  // every internal matrix dimension / leading dimension is a multiple of this
+
+struct gpk_handle_s {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    // grow-only device arenas (A: factor / K^-1, B: L^-1, T: GEMM scratch, misc: small vectors)
+    void* arena[8];
+    size_t arena_bytes[8];
+    double* h_pinned;  // 4096 doubles of pinned host scratch
+    int* d_info;       // device int: first failing minor of the last factorisation
+    int last_info;
+    int64_t launches;
+    unsigned func_cfg;  // bitmask: kernels whose dynamic-smem attribute has been set on this device
+    char err[512];
+};
+
+enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7 };
+
+int gpk_set_error(gpk_handle h, int status, const char* fmt, ...);
+// returns device pointer to at least `bytes` bytes in arena `which` (contents undefined after growth)
+void* gpk_arena(gpk_handle h, int which, size_t bytes);
+
+#define GPK_CUDA(h, call)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return gpk_set_error((h), e__ == cudaErrorMemoryAllocation ? GPK_ENOMEM : GPK_ECUDA,  \
+                                 "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define GPK_LAUNCH_CHECK(h)                                                                       \
+    do {                                                                                          \
+        (h)->launches++;                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess)                                                                   \
+            return gpk_set_error((h), GPK_ECUDA, "kernel launch failed: %s (%s:%d)",              \
+                                 cudaGetErrorString(e__), __FILE__, __LINE__);                    \
+    } while (0)
+
+static inline int gpk_pad(int n) { return (n + GPK_TILE - 1) / GPK_TILE * GPK_TILE; }
+
+// ---------------------------------------------------------------------------------------------
+// DMMA GEMM (gpk_gemm.cu).  Computes, for every 128x128 tile selected by `tri_out`,
+//     D(r,s) = alpha * sum_{k in [kbeg,kend)} P(r,k) * Q(s,k) + beta * Cin(r,s)
+// with D(r,s) stored at D[s + r*ldd] (s contiguous).  For a column-major C (M x N) this is D = C^t:
+// r is C's column index, s is C's row index.
+//   p_kcontig: P(r,k) at P[k + r*ldp]   else P[r + k*ldp]
+//   q_kcontig: Q(s,k) at Q[k + s*ldq]   else Q[s + k*ldq]
+// k-range per tile (tile-granular exploitation of triangular operands):
+//   kbeg = max(kb_r ? r0 : 0, kb_s ? s0 : 0);  kend = min(K, ke_r ? r0+128 : K, ke_s ? s0+128 : K)
+// tri_out: only tiles with s0 >= r0 are computed (lower triangle of the column-major C).
+// R, S multiples of 128; K multiple of 16; pointers 16-byte aligned; ld's even.
+// ---------------------------------------------------------------------------------------------
+struct GemmDesc {
+    const double* P; int64_t ldp; int64_t strideP;
+    const double* Q; int64_t ldq; int64_t strideQ;
+    double* D; int64_t ldd; int64_t strideD;
+    const double* Cin; int64_t ldc; int64_t strideC;
+    int R, S, K;
+    int batch;
+    double alpha, beta;
+    int p_kcontig, q_kcontig;
+    int tri_out;
+    int kb_r, kb_s, ke_r, ke_s;
+    int heavy_last;  // reverse tile order (heavy tiles are at high indices)
+};
+static inline GemmDesc gemm_desc() {
+    GemmDesc g;
+    memset(&g, 0, sizeof(g));
+    g.batch = 1; g.alpha = 1.0; g.beta = 0.0;
+    return g;
+}
+int gpk_gemm(gpk_handle h, const GemmDesc& g);
+
+// ---------------------------------------------------------------------------------------------
+// covariance (gpk_cov.cu)
+// ---------------------------------------------------------------------------------------------
+#define GPK_MAX_D 64
+struct CovParams {
+    int D;
+    double sf2;          // signalVar*signalVar
+    double sn2;          // noiseVar*noiseVar
+    double extra_diag;   // Option sigmaNoise (un-squared), 0 when None
+    double inv_ls2[GPK_MAX_D];  // 1/(ls*ls)
+};
+int gpk_make_cov_params(gpk_handle h, const double* theta, int D, int has_sigma_noise, double sigma_noise, CovParams* out);
+// full symmetric n x n (mirrored) into K (ld ldk)
+int gpk_cov_sym_full(gpk_handle h, const double* dX, int n, int64_t ldx, const CovParams& cp, double* dK, int64_t ldk);
+// lower tiles only of the padded N x N matrix (N = gpk_pad(n)); padding = identity
+int gpk_cov_sym_lower_padded(gpk_handle h, const double* dX, int n, int64_t ldx, const CovParams& cp, double* dK, int N);
+// rectangular m x n, no noise; rows>=m / cols>=n up to (mp, np) are zero-filled when mp/np > m/n
+int gpk_cov_cross(gpk_handle h, const double* dX1, int m, int64_t ldx1, const double* dX2, int n, int64_t ldx2,
+                  const CovParams& cp, double* dK, int64_t ldk, int mp, int np);
+int gpk_cov_deriv(gpk_handle h, int param_num, const double* dX, int n, int64_t ldx, const CovParams& cp,
+                  double sf, double sn, const double* ls_host, double* dK, int64_t ldk);
+
+// ---------------------------------------------------------------------------------------------
+// factorisation (gpk_chol.cu): A (N x N, ld N, lower, padded) -> L in place (lower part; when
+// keep_L is 0 the off-diagonal blocks of A are left in an unspecified state, only diag(L) and the
+// diagonal 128-blocks are valid), Li = L^-1 (N x N, ld N, lower; upper parts of diagonal blocks zeroed;
+// blocks above the diagonal untouched).  T: scratch of at least gpk_chol_scratch_doubles(N).
+// ---------------------------------------------------------------------------------------------
+size_t gpk_chol_scratch_doubles(int N);
+int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int col_offset);
+// L^-1 for a given lower-triangular L (N x N padded, ld N)
+int gpk_trtri_lower(gpk_handle h, const double* L, double* Li, double* T, int N);
+// Kinv (lower triangle incl. diagonal tiles in full) = Li^t Li
+int gpk_lauum_lower(gpk_handle h, const double* Li, double* Kinv, int N);
+
+// ---------------------------------------------------------------------------------------------
+// vectors / reductions / gradient (gpk_vec.cu, gpk_grad.cu)
+// ---------------------------------------------------------------------------------------------
+// z = Li * y (lower-triangular matvec, N padded; y has N entries with zeros in the padding)
+int gpk_trmv_lower(gpk_handle h, const double* Li, int N, const double* y, double* z, double* scratch);
+// a = Li^t * z
+int gpk_trmv_lower_t(gpk_handle h, const double* Li, int N, const double* z, double* a);
+// out[c] = sum_r M[r + c*ld] * v[r]  (square != 0: sum_r M[r + c*ld]^2), one warp per column
+int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int cols, const double* v, double* out, int square);
+// out[0] = -0.5*y.alpha - sum_{i<n} log(diag_i(A)) - 0.5*n*log(2 pi)   (GpPredictor.scala:144-149)
+int gpk_loglik(gpk_handle h, const double* A, int N, int n, const double* y, const double* alpha, double* out);
+// g[p] = 0.5 * sum_{i,j<n} (alpha_i alpha_j - Kinv_ij) * dk_p(x_i,x_j,i==j)  for p < nparams
+int gpk_grad_trace(gpk_handle h, const double* Kinv, int N, const double* dX, int n, int64_t ldx, const double* alpha,
+                   const CovParams& cp, double sf, double sn, const double* ls_host, int nparams, double* g_out,
+                   double* scratch);
+size_t gpk_grad_scratch_doubles(int N, int D);
+
+// misc elementwise helpers (gpk_vec.cu)
+int gpk_copy2d(gpk_handle h, double* dst, int64_t ldd, const double* src, int64_t lds, int rows, int cols);
+int gpk_pad_vector(gpk_handle h, double* dst, int N, const double* src, int n);
+// dst (N x N padded, lower + identity padding) from src (n x n, ld lds); optionally checks symmetry -> d_flag
+int gpk_load_sym_padded(gpk_handle h, double* dst, int N, const double* src, int n, int64_t lds, int* d_notsym);
+// dst (n x n, ld) = lower triangle of src (N x N) with zeros above the diagonal
+int gpk_store_lower(gpk_handle h, double* dst, int64_t ldd, const double* src, int N, int n);
+int gpk_store_tri(gpk_handle h, double* dst, int64_t ldd, const double* src, int N, int n, int transpose);
+int gpk_load_tri_padded(gpk_handle h, double* dst, int N, const double* src, int n, int64_t lds, int transpose_in);

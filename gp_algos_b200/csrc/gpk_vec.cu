@@ -1,0 +1,190 @@
+// gpk_vec.cu -- O(n^2) / O(n) pieces of the path: triangular matrix-vector products (the alpha = L^-t (L^-1 y)
+// solves of GpPredictor.scala:121-122, done with the explicit inverse that gpk_chol.cu produces), the
+// log-marginal-likelihood reduction (GpPredictor.scala:144-149), padding / triangle copies at the ABI.
+// All reductions are order-deterministic (no floating-point atomics).
+#include "gpk_internal.cuh"
+
+namespace {
+
+constexpr int KCH = 1024;  // k-chunk of the split-k lower matvec
+
+// partial[chunk][r] = sum_{k in chunk, k < rowblock_end} Li[r + k*N] * y[k]
+__global__ void __launch_bounds__(128) trmv_lower_partial(const double* __restrict__ Li, int N, const double* __restrict__ y,
+                                                          double* __restrict__ partial) {
+    const int rb = blockIdx.x, ch = blockIdx.y;
+    const int k0 = ch * KCH;
+    const int rend = (rb + 1) * GPK_TILE;
+    if (k0 >= rend) return;
+    const int k1 = min(k0 + KCH, rend);
+    const int r = rb * GPK_TILE + threadIdx.x;
+    const double* col = Li + r + (int64_t)k0 * N;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {
+        a0 += col[0] * y[k];
+        a1 += col[N] * y[k + 1];
+        a2 += col[2 * (int64_t)N] * y[k + 2];
+        a3 += col[3 * (int64_t)N] * y[k + 3];
+        col += 4 * (int64_t)N;
+    }
+    for (; k < k1; ++k) { a0 += col[0] * y[k]; col += N; }
+    partial[(int64_t)ch * N + r] = (a0 + a1) + (a2 + a3);
+}
+
+__global__ void trmv_lower_finish(const double* __restrict__ partial, int N, double* __restrict__ z) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const int rend = (r / GPK_TILE + 1) * GPK_TILE;
+    double acc = 0.0;
+    for (int ch = 0; ch * KCH < rend; ++ch) acc += partial[(int64_t)ch * N + r];
+    z[r] = acc;
+}
+
+// out[c] = sum_{r >= rstart(c)} M[r + c*ld] * v[r]; one warp per column.  tri != 0: rstart = 128-block of c.
+__global__ void __launch_bounds__(256) colwise_dot(const double* __restrict__ M, int64_t ld, int rows, int cols,
+                                                   const double* __restrict__ v, double* __restrict__ out, int tri,
+                                                   int square) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= cols) return;
+    const int lane = threadIdx.x & 31;
+    const int rs = tri ? (c / GPK_TILE) * GPK_TILE : 0;
+    const double* col = M + (int64_t)c * ld;
+    double a0 = 0, a1 = 0;
+    int r = rs + lane;
+    for (; r + 32 < rows; r += 64) {
+        const double m0 = col[r], m1 = col[r + 32];
+        a0 += m0 * (square ? m0 : v[r]);
+        a1 += m1 * (square ? m1 : v[r + 32]);
+    }
+    if (r < rows) { const double m0 = col[r]; a0 += m0 * (square ? m0 : v[r]); }
+    double a = a0 + a1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) out[c] = a;
+}
+
+__global__ void __launch_bounds__(256) loglik_kernel(const double* __restrict__ A, int N, int n, const double* __restrict__ y,
+                                                     const double* __restrict__ alpha, double* __restrict__ out) {
+    __shared__ double sd[256], sl[256];
+    double d = 0.0, l = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        d += y[i] * alpha[i];
+        l += log(A[i + (int64_t)i * N]);
+    }
+    sd[threadIdx.x] = d; sl[threadIdx.x] = l;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sd[threadIdx.x] += sd[threadIdx.x + s]; sl[threadIdx.x] += sl[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = -0.5 * sd[0] - sl[0] - 0.5 * n * log(2.0 * 3.14159265358979323846);
+}
+
+__global__ void pad_vector_kernel(double* dst, int N, const double* src, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) dst[i] = (i < n) ? src[i] : 0.0;
+}
+
+// dst (N x N): lower triangle (and full diagonal 128-blocks) of the symmetric src, identity padding.
+__global__ void load_sym_padded_kernel(double* dst, int N, const double* src, int n, int64_t lds, int* notsym) {
+    const int r = blockIdx.y * blockDim.x + threadIdx.x, c = blockIdx.x;
+    if (r >= N) return;
+    double v;
+    if (r < n && c < n) {
+        v = src[r + (int64_t)c * lds];
+        if (notsym != nullptr && r > c && v != src[c + (int64_t)r * lds]) *notsym = 1;
+    } else {
+        v = (r == c) ? 1.0 : 0.0;
+    }
+    dst[r + (int64_t)c * N] = v;
+}
+
+// triangular load: dst (N x N) lower-triangular with identity padding; transpose_in: src holds the upper factor
+__global__ void load_tri_padded_kernel(double* dst, int N, const double* src, int n, int64_t lds, int transpose_in) {
+    const int r = blockIdx.y * blockDim.x + threadIdx.x, c = blockIdx.x;
+    if (r >= N) return;
+    double v = 0.0;
+    if (r < n && c < n) {
+        if (r >= c) v = transpose_in ? src[c + (int64_t)r * lds] : src[r + (int64_t)c * lds];
+    } else if (r == c) {
+        v = 1.0;
+    }
+    dst[r + (int64_t)c * N] = v;
+}
+
+// dst (n x n, ld) = tri(src): lower triangle of src (transpose == 0) or its transpose into the upper triangle
+__global__ void store_tri_kernel(double* dst, int64_t ldd, const double* src, int N, int n, int transpose) {
+    const int r = blockIdx.y * blockDim.x + threadIdx.x, c = blockIdx.x;
+    if (r >= n || c >= n) return;
+    double v = 0.0;
+    if (!transpose) { if (r >= c) v = src[r + (int64_t)c * N]; }
+    else            { if (c >= r) v = src[c + (int64_t)r * N]; }
+    dst[r + (int64_t)c * ldd] = v;
+}
+
+}  // namespace
+
+int gpk_trmv_lower(gpk_handle h, const double* Li, int N, const double* y, double* z, double* scratch) {
+    dim3 grid(N / GPK_TILE, (N + KCH - 1) / KCH);
+    trmv_lower_partial<<<grid, 128, 0, h->stream>>>(Li, N, y, scratch);
+    GPK_LAUNCH_CHECK(h);
+    trmv_lower_finish<<<(N + 255) / 256, 256, 0, h->stream>>>(scratch, N, z);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_trmv_lower_t(gpk_handle h, const double* Li, int N, const double* z, double* a) {
+    colwise_dot<<<(N + 7) / 8, 256, 0, h->stream>>>(Li, N, N, N, z, a, 1, 0);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int cols, const double* v, double* out, int square) {
+    if (cols <= 0) return GPK_OK;
+    colwise_dot<<<(cols + 7) / 8, 256, 0, h->stream>>>(M, ld, rows, cols, v, out, 0, square);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_loglik(gpk_handle h, const double* A, int N, int n, const double* y, const double* alpha, double* out) {
+    loglik_kernel<<<1, 256, 0, h->stream>>>(A, N, n, y, alpha, out);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_copy2d(gpk_handle h, double* dst, int64_t ldd, const double* src, int64_t lds, int rows, int cols) {
+    if (rows <= 0 || cols <= 0) return GPK_OK;
+    GPK_CUDA(h, cudaMemcpy2DAsync(dst, ldd * sizeof(double), src, lds * sizeof(double), (size_t)rows * sizeof(double),
+                                  (size_t)cols, cudaMemcpyDeviceToDevice, h->stream));
+    h->launches++;
+    return GPK_OK;
+}
+
+int gpk_pad_vector(gpk_handle h, double* dst, int N, const double* src, int n) {
+    pad_vector_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(dst, N, src, n);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_load_sym_padded(gpk_handle h, double* dst, int N, const double* src, int n, int64_t lds, int* d_notsym) {
+    load_sym_padded_kernel<<<dim3(N, (N + 127) / 128), 128, 0, h->stream>>>(dst, N, src, n, lds, d_notsym);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_load_tri_padded(gpk_handle h, double* dst, int N, const double* src, int n, int64_t lds, int transpose_in) {
+    load_tri_padded_kernel<<<dim3(N, (N + 127) / 128), 128, 0, h->stream>>>(dst, N, src, n, lds, transpose_in);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_store_tri(gpk_handle h, double* dst, int64_t ldd, const double* src, int N, int n, int transpose) {
+    if (n <= 0) return GPK_OK;
+    store_tri_kernel<<<dim3(n, (n + 127) / 128), 128, 0, h->stream>>>(dst, ldd, src, N, n, transpose);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_store_lower(gpk_handle h, double* dst, int64_t ldd, const double* src, int N, int n) {
+    return gpk_store_tri(h, dst, ldd, src, N, n, 0);
+}

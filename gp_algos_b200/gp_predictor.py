@@ -1,0 +1,194 @@
+"""Host mirror of gp/regression/GpPredictor.scala over libgpk's fused C-ABI entry points."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .kernel_requisites import GaussianRbfKernel, GaussianRbfParams
+
+
+@dataclass
+class GaussianDistribution:
+    """utils/StatsUtils.scala:19-21."""
+    mean: np.ndarray
+    sigma: np.ndarray
+
+    @property
+    def dim(self) -> int:
+        return len(self.mean)
+
+
+@dataclass
+class PredictionTrainingInput:
+    """GpPredictor.scala:171-172."""
+    trainingData: np.ndarray
+    sigmaNoise: Optional[float]
+    targets: np.ndarray
+
+
+@dataclass
+class PredictionInput:
+    """GpPredictor.scala:162-169."""
+    trainingData: np.ndarray
+    testData: np.ndarray
+    sigmaNoise: Optional[float]
+    targets: np.ndarray
+
+    @property
+    def toPredictionTrainingInput(self) -> PredictionTrainingInput:
+        return PredictionTrainingInput(self.trainingData, self.sigmaNoise, self.targets)
+
+
+def _theta_of(hyperParams) -> np.ndarray:
+    if isinstance(hyperParams, GaussianRbfParams):
+        return np.ascontiguousarray(hyperParams.toDenseVector)
+    return np.ascontiguousarray(np.asarray(hyperParams, dtype=np.float64))
+
+
+class GpPredictor:
+    """GpPredictor.scala:15: constructed from a kernel function (same one-argument constructor the Spring
+    beans use, spring-context.xml:33-51)."""
+
+    def __init__(self, kernelFunc: GaussianRbfKernel, handle: _lib.Handle | None = None):
+        if not isinstance(kernelFunc, GaussianRbfKernel):
+            raise TypeError("only GaussianRbfKernel is lowered to the GPU path")
+        self.kernelFunc = kernelFunc
+        self._handle = handle
+
+    @property
+    def handle(self) -> _lib.Handle:
+        if self._handle is None:
+            self._handle = _lib.default_handle()
+        return self._handle
+
+    @staticmethod
+    def _xy(trainingData, targets):
+        X = _lib.fmat(trainingData)
+        y = _lib.fmat(targets)
+        if X.shape[0] != len(y):  # require(...) GpPredictor.scala:108
+            raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, "requirement failed: Number of objects in training data "
+                                            "matrix should be equal to targets vector length")
+        return X, y
+
+    # ---- GpPredictor.scala:104-124 (+ overload :89-94) ------------------------------------------------
+    def preComputeComponents(self, trainingData, sigmaNoise, targets, hyperParams=None):
+        """-> (L, alphaVec, Option[noise * I]).  Like the reference, the third element is a dense n x n matrix
+        when sigmaNoise is defined (GpPredictor.scala:116-117); it is built lazily on the host."""
+        h = self.handle
+        theta = _theta_of(hyperParams if hyperParams is not None else self.kernelFunc.hyperParams)
+        X, y = self._xy(trainingData, targets)
+        n, D = X.shape
+        if len(theta) != D + 2:
+            raise ValueError(f"requirement failed: {len(theta)} does not equal to {D + 2}")
+        L = np.empty((n, n), order="F")
+        alpha = np.empty(n)
+        ll = C.c_double()
+        h.check(h.lib.gpk_gp_fit(h.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(theta), int(sigmaNoise is not None),
+                                 float(sigmaNoise or 0.0), _lib.ptr(L), n, _lib.ptr(alpha), C.addressof(ll)))
+        noise = None if sigmaNoise is None else np.eye(n) * sigmaNoise
+        return L, alpha, noise
+
+    # ---- GpPredictor.scala:60-80 ----------------------------------------------------------------------
+    def logLikelihoodWithDerivatives(self, input: PredictionTrainingInput, hyperParams, optimizedParamsNum: int):
+        h = self.handle
+        theta = _theta_of(hyperParams)
+        X, y = self._xy(input.trainingData, input.targets)
+        n, D = X.shape
+        if len(theta) != D + 2:
+            raise ValueError(f"requirement failed: {len(theta)} does not equal to {D + 2}")
+        ll = C.c_double()
+        g = np.zeros(max(optimizedParamsNum, 1))
+        s = input.sigmaNoise
+        h.check(h.lib.gpk_gp_nll_grad(h.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(theta), int(s is not None),
+                                      float(s or 0.0), int(optimizedParamsNum), C.addressof(ll), _lib.ptr(g)))
+        return ll.value, g[:optimizedParamsNum]
+
+    # ---- GpPredictor.scala:24-43 ----------------------------------------------------------------------
+    def predict(self, input: PredictionInput, hyperParams=None):
+        h = self.handle
+        theta = _theta_of(hyperParams if hyperParams is not None else self.kernelFunc.hyperParams)
+        X, y = self._xy(input.trainingData, input.targets)
+        Xs = _lib.fmat(input.testData)
+        n, D = X.shape
+        m = Xs.shape[0]
+        mean = np.empty(m)
+        sigma = np.empty((m, m), order="F")
+        ll = C.c_double()
+        s = input.sigmaNoise
+        h.check(h.lib.gpk_gp_predict(h.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(Xs), m, m, _lib.ptr(theta),
+                                     int(s is not None), float(s or 0.0), _lib.ptr(mean), _lib.ptr(sigma), m, C.addressof(ll)))
+        return GaussianDistribution(mean, sigma), ll.value
+
+    # ---- GpPredictor.scala:45-58 ----------------------------------------------------------------------
+    def computePosterior(self, trainingData, testData, l, alphaVec, kernelFunc=None):
+        """-> (GaussianDistribution(mean, sigma), vMatrix).  The factor `l` is adopted on the device
+        (its inverse is formed once) -- use FittedGp for the fit-once / predict-many pattern."""
+        kf = kernelFunc or self.kernelFunc
+        model = FittedGp.from_factor(self.handle, trainingData, l, alphaVec, kf)
+        try:
+            return model.computePosterior(testData)
+        finally:
+            model.close()
+
+    def fit(self, trainingData, sigmaNoise, targets, hyperParams=None) -> "FittedGp":
+        """Device-resident preComputeComponents: the GP-UKF / GP-UCB call pattern
+        (GPUnscentedKalmanFilter.scala:77-88,123-147) without moving L across PCIe."""
+        theta = _theta_of(hyperParams if hyperParams is not None else self.kernelFunc.hyperParams)
+        return FittedGp.fit(self.handle, trainingData, targets, theta, sigmaNoise)
+
+
+class FittedGp:
+    """Opaque device token for (X, L^-1, alpha, theta) -- SURVEY.md 8(b) 'ownership'."""
+
+    def __init__(self, handle, token, n, D, ll=None):
+        self.handle, self._m, self.n, self.D, self.logLikelihood = handle, token, n, D, ll
+
+    @classmethod
+    def fit(cls, handle, trainingData, targets, theta, sigmaNoise=None):
+        X, y = GpPredictor._xy(trainingData, targets)
+        n, D = X.shape
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        tok = C.c_void_p()
+        ll = C.c_double()
+        handle.check(handle.lib.gpk_gp_model_fit(handle.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(theta),
+                                                 int(sigmaNoise is not None), float(sigmaNoise or 0.0), C.byref(tok),
+                                                 C.addressof(ll)))
+        return cls(handle, tok, n, D, ll.value)
+
+    @classmethod
+    def from_factor(cls, handle, trainingData, l, alphaVec, kernelFunc):
+        X = _lib.fmat(trainingData)
+        L = _lib.fmat(l)
+        a = _lib.fmat(alphaVec)
+        n, D = X.shape
+        theta = np.ascontiguousarray(kernelFunc.theta)
+        tok = C.c_void_p()
+        handle.check(handle.lib.gpk_gp_model_from_factor(handle.h, _lib.ptr(X), n, D, n, _lib.ptr(L), n, _lib.ptr(a),
+                                                         _lib.ptr(theta), C.byref(tok)))
+        return cls(handle, tok, n, D)
+
+    def computePosterior(self, testData, full_cov: bool = True, want_v: bool = True):
+        Xs = _lib.fmat(testData)
+        m = Xs.shape[0]
+        mean = np.empty(m)
+        sigma = np.empty((m, m), order="F") if full_cov else np.empty(m)
+        V = np.empty((self.n, m), order="F") if want_v else None
+        self.handle.check(self.handle.lib.gpk_gp_model_predict(
+            self.handle.h, self._m, _lib.ptr(Xs), m, m, int(full_cov), _lib.ptr(mean), _lib.ptr(sigma), m,
+            _lib.ptr(V) if want_v else None, self.n))
+        return GaussianDistribution(mean, sigma), V
+
+    def close(self):
+        if self._m:
+            self.handle.lib.gpk_gp_model_destroy(self.handle.h, self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

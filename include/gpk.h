@@ -1,0 +1,129 @@
+/*
+ * gpk.h -- C ABI of libgpk: the B200-native (sm_100a) dense FP64 Gaussian-process linear algebra
+ * that replaces the hot path of astroHaoPeng/gp_algos.  No torch types, no C++ types: plain pointers
+ * and sizes, so the same entry points can be bound from Scala/JVM (JNA / JNI / Java FFM), Python
+ * (ctypes) or C.  See INTEGRATION.md for the reference-side bindings.
+ *
+ * Conventions:
+ *   - every matrix is COLUMN-MAJOR FP64 with an explicit leading dimension (Breeze DenseMatrix
+ *     layout: element (r,c) at base[r + c*ld]); vectors are contiguous.
+ *   - theta is the reference's hyper-parameter packing [signalVar, lengthScale_1..D, noiseVar]
+ *     (utils/KernelRequisites.scala:39-58), length D+2.  signalVar/noiseVar are std-dev-like and
+ *     squared inside the kernel (KernelRequisites.scala:66-72).
+ *   - functions without a suffix take HOST pointers, copy in/out and return when results are on
+ *     the host (synchronous, like the Scala functions they replace).  Functions ending in `_dev`
+ *     take DEVICE pointers, enqueue on the handle's stream and return without synchronising
+ *     (scalars are written to device memory the caller provides).
+ *   - all functions return 0 on success or a negative gpk_status; gpk_last_error(h) gives text.
+ *     There is NO CPU fallback anywhere in this library.
+ *
+ * Reference paths below are relative to /root/reference/src/main/scala/.
+ */
+#ifndef GPK_H
+#define GPK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpk_handle_s* gpk_handle;
+
+enum gpk_status {
+    GPK_OK = 0,
+    GPK_EINVAL = -1,   /* IllegalArgumentException (require(...) at GpPredictor.scala:108, MatrixUtils.scala:125) */
+    GPK_ENOTSYM = -2,  /* breeze MatrixNotSymmetricException from `cholesky` */
+    GPK_ENOTPD = -3,   /* breeze NotConvergedException from `cholesky`; gpk_last_info(h) = failing minor (1-based) */
+    GPK_ECUDA = -4,    /* CUDA runtime error */
+    GPK_ENOMEM = -5    /* device allocation failed */
+};
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* One handle = one device + one stream + a grow-only device workspace. Not re-entrant; use one
+ * handle per host thread / per GPU.  `stream` may be NULL (the handle creates its own) or a
+ * cudaStream_t owned by the caller (e.g. torch.cuda.current_stream().cuda_stream). */
+int gpk_create(gpk_handle* out, int device, void* stream);
+int gpk_destroy(gpk_handle h);
+const char* gpk_last_error(gpk_handle h);
+int gpk_last_info(gpk_handle h);
+int gpk_synchronize(gpk_handle h);
+/* number of kernel launches issued through this handle since creation (bench.py "gpu_launches") */
+int64_t gpk_launch_count(gpk_handle h);
+const char* gpk_version(void);
+
+/* ---- fine-grained MatrixUtils replacements ---------------------------------------------------- */
+/* utils/MatrixUtils.scala:57-70  buildKernelMatrix(kernel, data): symmetric n x n,
+ * K(i,j) = sf^2 exp(-1/2 sum_d (x_id-x_jd)^2/l_d^2) + sn^2 [i==j]; lower triangle computed, mirrored. */
+int gpk_cov_se_ard(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* theta,
+                   double* K, int64_t ldk);
+int gpk_cov_se_ard_dev(gpk_handle h, const double* dX, int n, int D, int64_t ldx, const double* theta_host,
+                       double* dK, int64_t ldk);
+/* utils/MatrixUtils.scala:44-55,86-97  buildKernelMatrix(kernel, in1, in2): m x n, never adds noise. */
+int gpk_cov_cross_se_ard(gpk_handle h, const double* X1, int m, int64_t ldx1, const double* X2, int n,
+                         int64_t ldx2, int D, const double* theta, double* K, int64_t ldk);
+int gpk_cov_cross_se_ard_dev(gpk_handle h, const double* dX1, int m, int64_t ldx1, const double* dX2, int n,
+                             int64_t ldx2, int D, const double* theta_host, double* dK, int64_t ldk);
+/* utils/MatrixUtils.scala:72-84 with f = derAfterHyperParam(param_num) (KernelRequisites.scala:76-86;
+ * param_num is 1-based like the reference).  Provided for API completeness/tests: the fused
+ * gradient (gpk_gp_nll_grad) never materialises these matrices. */
+int gpk_cov_deriv_se_ard(gpk_handle h, int param_num, const double* X, int n, int D, int64_t ldx,
+                         const double* theta, double* dK, int64_t ldk);
+
+/* breeze `cholesky` at GpPredictor.scala:120 / EpParameterEstimator.scala:58 (LAPACK dpotrf 'L'):
+ * A n x n symmetric -> L lower with strict upper zeroed.  check_symmetric != 0 reproduces Breeze's
+ * exact-symmetry test (GPK_ENOTSYM).  GPK_ENOTPD + gpk_last_info on a non-positive pivot. */
+int gpk_potrf_lower(gpk_handle h, const double* A, int n, int64_t lda, double* L, int64_t ldl,
+                    int check_symmetric);
+/* utils/MatrixUtils.scala:17-35,115-133  forwardSolve / backSolve, vector or matrix right-hand side.
+ * `T` is the triangular matrix as stored (n x n, column-major); transposed != 0 means the operand is
+ * T^t (the `L.t` view of GpPredictor.scala:122).  upper != 0 selects backSolve semantics (the
+ * EFFECTIVE operand is upper triangular), otherwise forwardSolve (effective operand lower). */
+int gpk_trsm(gpk_handle h, int upper, int transposed, const double* T, int n, int64_t ldt,
+             const double* B, int nrhs, int64_t ldb, double* Xout, int64_t ldx);
+/* utils/MatrixUtils.scala:106-113  invTriangular(matrix, isUpper): dense n x n inverse. */
+int gpk_trtri(gpk_handle h, int is_upper, const double* T, int n, int64_t ldt, double* Tinv, int64_t ldi);
+
+/* ---- fused GpPredictor replacements ----------------------------------------------------------- */
+/* gp/regression/GpPredictor.scala:104-124 preComputeComponents + :144-149 logLikelihood.
+ * has_sigma_noise/sigma_noise mirror Option[Double]; it is added UN-squared to the diagonal
+ * (GpPredictor.scala:116-117).  Outputs: L (n x n, may be NULL), alpha (n), ll (1). */
+int gpk_gp_fit(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y,
+               const double* theta, int has_sigma_noise, double sigma_noise, double* L, int64_t ldl,
+               double* alpha, double* ll);
+/* gp/regression/GpPredictor.scala:60-80 logLikelihoodWithDerivatives: ll and g[nparams],
+ * g_p = 1/2 tr((alpha alpha^t - K^-1) dK/dtheta_{p+1}).  K, L, L^-1, K^-1 never leave the device
+ * and dK/dtheta is never materialised. */
+int gpk_gp_nll_grad(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y,
+                    const double* theta, int has_sigma_noise, double sigma_noise, int nparams,
+                    double* ll, double* grad);
+/* Same with X (n x D, ld ldx) and y resident on the device; out_dev[0] = ll, out_dev[1..nparams] = g.
+ * Asynchronous on the handle's stream; *info_dev (int, device) receives 0 or the failing minor. */
+int gpk_gp_nll_grad_dev(gpk_handle h, const double* dX, int n, int D, int64_t ldx, const double* dy,
+                        const double* theta_host, int has_sigma_noise, double sigma_noise, int nparams,
+                        double* out_dev, int* info_dev);
+
+/* Resident fitted model (GP-UKF / GP-UCB call pattern, GPUnscentedKalmanFilter.scala:77-88,123-147):
+ * fit once, keep X, L^-1 and alpha on the device, predict many times. */
+typedef struct gpk_model_s* gpk_model;
+int gpk_gp_model_fit(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y,
+                     const double* theta, int has_sigma_noise, double sigma_noise, gpk_model* out, double* ll);
+/* Adopt an existing factor (computePosterior(trainingData,testData,l,alphaVec,kernelFunc),
+ * GpPredictor.scala:50-58, is handed L and alpha by its caller). */
+int gpk_gp_model_from_factor(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* L,
+                             int64_t ldl, const double* alpha, const double* theta, gpk_model* out);
+int gpk_gp_model_destroy(gpk_handle h, gpk_model m);
+/* gp/regression/GpPredictor.scala:45-58 computePosterior: mean (m), sigma (m x m full if
+ * want_full_cov, else only the diagonal in sigma[0..m-1]), V = L^-1 K*^t (n x m, may be NULL).
+ * The sigma diagonal includes noiseVar^2 (MatrixUtils.scala:63 via GpPredictor.scala:56). */
+int gpk_gp_model_predict(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_t ldxs,
+                         int want_full_cov, double* mean, double* sigma, int64_t lds, double* V, int64_t ldv);
+/* gp/regression/GpPredictor.scala:24-43 predict: fit + computePosterior (+ sigma_noise * I) + ll. */
+int gpk_gp_predict(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y,
+                   const double* Xs, int ms, int64_t ldxs, const double* theta, int has_sigma_noise,
+                   double sigma_noise, double* mean, double* sigma, int64_t lds, double* ll);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPK_H */
