@@ -73,6 +73,7 @@ def load():
         lib.gpk_potrf_lower.argtypes = [vp, vp, ci, _i64, vp, _i64, ci]
         lib.gpk_trsm.argtypes = [vp, ci, ci, vp, ci, _i64, vp, ci, _i64, vp, _i64]
         lib.gpk_trtri.argtypes = [vp, ci, vp, ci, _i64, vp, _i64]
+        lib.gpk_syrk_lower_dev.argtypes = [vp, vp, _i64, vp, _i64, ci, ci]
         lib.gpk_gp_fit.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, cd, vp, _i64, vp, vp]
         lib.gpk_gp_nll_grad.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, cd, ci, vp, vp]
         lib.gpk_gp_nll_grad_dev.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, cd, ci, vp, vp]

@@ -359,6 +359,15 @@ int gpk_trsm(gpk_handle h, int upper, int transposed, const double* T, int n, in
     return gpk_synchronize(h);
 }
 
+int gpk_syrk_lower_dev(gpk_handle h, const double* dP, int64_t ldp, double* dC, int64_t ldc, int n, int k) {
+    if (!h || n <= 0 || k <= 0) return gpk_set_error(h, GPK_EINVAL, "gpk_syrk_lower_dev: bad dimensions");
+    GemmDesc g = gemm_desc();
+    g.P = dP; g.ldp = ldp; g.Q = dP; g.ldq = ldp;
+    g.D = dC; g.ldd = ldc; g.Cin = dC; g.ldc = ldc;
+    g.R = n; g.S = n; g.K = k; g.alpha = -1.0; g.beta = 1.0; g.tri_out = 1;
+    return gpk_gemm(h, g);
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused GpPredictor paths
 // ------------------------------------------------------------------------------------------------
@@ -372,11 +381,13 @@ int gpk_gp_nll_grad_dev(gpk_handle h, const double* dX, int n, int D, int64_t ld
     CovParams cp;
     rc = fit_dev(h, dX, n, D, ldx, dy, theta, has_s, s, /*keep_L=*/0, fb, &cp, out_dev);
     if (rc) return rc;
-    rc = gpk_lauum_lower(h, fb.Li, fb.A, fb.N);  // K^-1 = L^-t L^-1 (GpPredictor.scala:67), lower tiles, into A
-    if (rc) return rc;
-    Theta t = unpack(theta, D);
-    rc = gpk_grad_trace(h, fb.A, fb.N, dX, n, ldx, fb.alpha, cp, t.sf, t.sn, t.ls, nparams, out_dev + 1, fb.scratch);
-    if (rc) return rc;
+    if (nparams > 0) {
+        rc = gpk_lauum_lower(h, fb.Li, fb.A, fb.N);  // K^-1 = L^-t L^-1 (GpPredictor.scala:67), lower tiles, into A
+        if (rc) return rc;
+        Theta t = unpack(theta, D);
+        rc = gpk_grad_trace(h, fb.A, fb.N, dX, n, ldx, fb.alpha, cp, t.sf, t.sn, t.ls, nparams, out_dev + 1, fb.scratch);
+        if (rc) return rc;
+    }
     if (info_dev) GPK_CUDA(h, cudaMemcpyAsync(info_dev, h->d_info, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
     return GPK_OK;
 }

@@ -84,6 +84,12 @@ int gpk_trsm(gpk_handle h, int upper, int transposed, const double* T, int n, in
 /* utils/MatrixUtils.scala:106-113  invTriangular(matrix, isUpper): dense n x n inverse. */
 int gpk_trtri(gpk_handle h, int is_upper, const double* T, int n, int64_t ldt, double* Tinv, int64_t ldi);
 
+/* The Cholesky trailing update on its own (device pointers, asynchronous): C(lower 128-tiles) -= P * P^t with
+ * C n x n (ldc) and P n x k (ldp) column-major, n a multiple of 128, k a multiple of 16, 16-byte aligned,
+ * even leading dimensions.  This is the DMMA kernel that carries ~all flops of gpk_potrf_lower; bench.py
+ * times it in isolation for the FP64 tensor roofline. */
+int gpk_syrk_lower_dev(gpk_handle h, const double* dP, int64_t ldp, double* dC, int64_t ldc, int n, int k);
+
 /* ---- fused GpPredictor replacements ----------------------------------------------------------- */
 /* gp/regression/GpPredictor.scala:104-124 preComputeComponents + :144-149 logLikelihood.
  * has_sigma_noise/sigma_noise mirror Option[Double]; it is added UN-squared to the diagonal

@@ -1,0 +1,106 @@
+"""CPU: the C-ABI library loads and exports every symbol include/gpk.h declares; the host mirror of
+KernelRequisites behaves like the reference's KernelRequisitesTest; the product never touches the oracle and
+fails loudly without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import gp_algos_b200 as gp
+from gp_algos_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.lib_path()):
+        import __graft_entry__ as ge
+        ge.build()
+    hdr = open(os.path.join(ROOT, "include", "gpk.h")).read()
+    names = sorted(set(re.findall(r"\b(gpk_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    lib = ctypes.CDLL(_lib.lib_path())
+    for nme in names:
+        assert hasattr(lib, nme), f"{nme} declared in include/gpk.h but not exported by libgpk.so"
+    assert b"sm_100a" in ctypes.c_char_p(ctypes.cast(lib.gpk_version, ctypes.CFUNCTYPE(ctypes.c_char_p))()).value
+
+
+def test_library_contains_sm100a_dmma_code():
+    out = subprocess.run(["cuobjdump", "-sass", _lib.lib_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    assert "DMMA.8x8x4" in out.stdout      # FP64 tensor path of the trailing update
+    assert "LDGSTS" in out.stdout          # cp.async operand staging
+
+
+def test_no_cpu_fallback_without_gpu():
+    if _have_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(gp.GpkError):
+        _lib.Handle(0)
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(1., np.ones(3), 0.))
+    with pytest.raises(gp.GpkError):
+        gp.MatrixUtils.buildKernelMatrix(kf, np.zeros((3, 3)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gp_algos_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "gp_oracle" not in src, f
+
+
+# ---- mirrors src/test/scala/utils/KernelRequisitesTest.scala:18-49 -------------------------------------
+def test_hyperparams_to_dense_vector():
+    hp = gp.GaussianRbfParams(signalVar=1., lengthScales=np.ones(5), noiseVar=0.)
+    assert np.array_equal(hp.toDenseVector, np.array([1., 1., 1., 1., 1., 1., 0.]))
+
+
+def test_hyperparams_get_at_position():
+    hp = gp.GaussianRbfParams(signalVar=1., lengthScales=np.array([5., 2., 3.]), noiseVar=0.)
+    assert [hp.getAtPosition(i) for i in range(1, 6)] == [1., 5., 2., 3., 0.]
+    with pytest.raises(LookupError):  # intercept[MatchError]
+        hp.getAtPosition(6)
+
+
+def test_kernel_updates_its_params():
+    ls = np.ones(5)
+    k0 = gp.GaussianRbfKernel(gp.GaussianRbfParams(1., ls, 0.))
+    assert k0.rbfParams == gp.GaussianRbfParams(1., ls, 0.)
+    k1 = k0.changeHyperParams(np.array([2., 3., 3., 3., 3., 3., 0.]))
+    assert k1.rbfParams == gp.GaussianRbfParams(2., ls * 3., 0.)
+    with pytest.raises(ValueError):  # require(...) KernelRequisites.scala:55
+        k0.changeHyperParams(np.ones(6))
+
+
+def test_scalar_kernel_matches_oracle():
+    from oracle import gp_oracle as orc
+    rng = np.random.default_rng(0)
+    th = orc.pack_theta(1.3, [0.5, 0.9, 2.0], 0.2)
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
+    X = rng.standard_normal((4, 3))
+    K = orc.lit_build_kernel_matrix(X, th)
+    for i in range(4):
+        for j in range(4):
+            assert abs(kf(X[i], X[j], i == j) - K[i, j]) <= 1e-14 * abs(K[i, j])
+    for p in range(1, 6):
+        dK = orc.lit_build_der_matrix(p, X, th)
+        f = kf.derAfterHyperParam(p)
+        assert abs(f(X[1], X[2], False) - dK[1, 2]) <= 1e-14 * max(abs(dK[1, 2]), 1e-300)
+    with pytest.raises(LookupError):
+        kf.derAfterHyperParam(6)
