@@ -164,7 +164,7 @@ def run_gpk(args):
         theta[0] *= 10 ** rng.uniform(-0.1, 0.1)
         theta[1:-1] *= 10 ** rng.uniform(-0.1, 0.1, size=DIM)
     # a real (non-default) torch stream shared with libgpk so torch.cuda.Event brackets the library's launches
-    tstream = torch.cuda.Stream()
+    tstream = torch.cuda.Stream(priority=-1)  # above libgpk's low-priority side streams
     torch.cuda.set_stream(tstream)
     h = _lib.Handle(local, tstream.cuda_stream)
     dX = torch.from_numpy(np.asfortranarray(X).T.copy()).cuda()  # (D, n) row-major == n x D column-major, ld n

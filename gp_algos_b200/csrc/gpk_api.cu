@@ -63,7 +63,10 @@ int gpk_create(gpk_handle* out, int device, void* stream) {
         h->stream = (cudaStream_t)stream;
         h->own_stream = false;
     } else {
-        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return GPK_ECUDA; }
+        // own main stream at the highest priority: its (critical-path) CTAs are scheduled before the side streams'
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, greatest) != cudaSuccess) { delete h; return GPK_ECUDA; }
         h->own_stream = true;
     }
     if (cudaMallocHost((void**)&h->h_pinned, 4096 * sizeof(double)) != cudaSuccess ||
@@ -72,6 +75,10 @@ int gpk_create(gpk_handle* out, int device, void* stream) {
         return GPK_ENOMEM;
     }
     cudaMemset(h->d_info, 0, 4 * sizeof(int));
+    for (int i = 0; i < GPK_NSIDE; ++i)
+        if (cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, 0 /* lowest */) != cudaSuccess) { delete h; return GPK_ECUDA; }
+    for (int i = 0; i < GPK_NEVENTS; ++i)
+        if (cudaEventCreateWithFlags(&h->evpool[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return GPK_ECUDA; }
     *out = h;
     return GPK_OK;
 }
@@ -84,6 +91,10 @@ int gpk_destroy(gpk_handle h) {
         if (h->arena[i]) cudaFree(h->arena[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->d_info) cudaFree(h->d_info);
+    for (int i = 0; i < GPK_NSIDE; ++i)
+        if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
+    for (int i = 0; i < GPK_NEVENTS; ++i)
+        if (h->evpool[i]) cudaEventDestroy(h->evpool[i]);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return GPK_OK;

@@ -10,130 +10,47 @@
 //     A22 -= L21 * L21^t                      (SYRK, lower tiles only)          <- the trailing update
 //     potrf_inv(A22, Li22)
 //     Li21 = -Li22 * (L21 * Li11)             (two triangular-aware GEMMs)
-//   base case n = 128: one CTA factors the block in shared memory and inverts it in place.
+//   base case n = 128: one CTA factors the block in shared memory and inverts it in place (gpk_base.cu).
 // Total n^3/3 (factor) + n^3/3 (inverse) flops; the K^-1 = Li^t Li product (another n^3/3, lower only)
 // is a single GEMM launch (gpk_lauum_lower).  Because L^-1 is a by-product, every triangular solve of
 // the path (alpha, V = L^-1 K*^t) becomes a matrix product as well.
 #include "gpk_internal.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int NB = GPK_TILE;  // 128
-constexpr int SLD = NB + 1;   // shared-memory column stride (odd -> conflict-free row walks)
-
-// One CTA of 128 threads; thread r owns row r.  mode 0: factor A (lower) -> L (written back to A,
-// lower incl. diagonal) and Li = L^-1;  mode 1: A already holds a lower-triangular L, only invert.
-// Li gets the full 128x128 block (zeros above the diagonal).  A non-positive pivot records
-// col_offset + j + 1 into *info (first failure wins) and poisons the block with NaN.
-__global__ void __launch_bounds__(NB) potf2_trti2_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ Li,
-                                                         int64_t ldi, int* info, int col_offset, int mode,
-                                                         int64_t strideA, int64_t strideLi) {
-    extern __shared__ double S[];  // S[r + c*SLD]
-    __shared__ double colbuf[NB];
-    __shared__ double piv_s;
-    A += blockIdx.x * strideA;
-    Li += blockIdx.x * strideLi;
-    col_offset += blockIdx.x * NB;
-    const int r = threadIdx.x;
-
-    for (int c = 0; c < NB; ++c) S[r + c * SLD] = (r >= c) ? A[r + (int64_t)c * lda] : 0.0;
-    __syncthreads();
-
-    if (mode == 0) {
-        for (int p = 0; p < NB / 32; ++p) {
-            const int j0 = 32 * p;
-            double a[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) a[c] = S[r + (j0 + c) * SLD];
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-                const int j = j0 + jj;
-                if (r == j) piv_s = a[jj];
-                __syncthreads();
-                const double piv = piv_s;
-                if (!(piv > 0.0) && r == j) atomicCAS(info, 0, col_offset + j + 1);
-                const double d = sqrt(piv);
-                if (r >= j) {
-                    a[jj] = (r == j) ? d : a[jj] / d;
-                    colbuf[r] = a[jj];
-                }
-                __syncthreads();
-                if (r > j) {
-                    const double l = a[jj];
-#pragma unroll
-                    for (int cc = jj + 1; cc < 32; ++cc)
-                        if (r >= j0 + cc) a[cc] -= l * colbuf[j0 + cc];
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) S[r + (j0 + c) * SLD] = (r >= j0 + c) ? a[c] : 0.0;
-            __syncthreads();
-            // trailing update of columns >= j0+32 with this 32-wide panel
-            if (r >= j0 + 32) {
-                for (int c = j0 + 32; c <= r; ++c) {
-                    double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 32; k += 2) {
-                        acc0 += a[k] * S[c + (j0 + k) * SLD];
-                        acc1 += a[k + 1] * S[c + (j0 + k + 1) * SLD];
-                    }
-                    S[r + c * SLD] -= (acc0 + acc1);
-                }
-            }
-            __syncthreads();
-        }
-        for (int c = 0; c < NB; ++c)
-            if (r >= c) A[r + (int64_t)c * lda] = S[r + c * SLD];
-        __syncthreads();
-    }
-
-    // in-place inverse of the lower-triangular S (LAPACK dtrti2 'L' ordering: last column first)
-    for (int j = NB - 1; j >= 0; --j) {
-        const double ajj = 1.0 / S[j + j * SLD];
-        double acc0 = 0.0, acc1 = 0.0;
-        if (r > j) {
-            int k = j + 1;
-            for (; k + 1 <= r; k += 2) {
-                acc0 += S[r + k * SLD] * S[k + j * SLD];
-                acc1 += S[r + (k + 1) * SLD] * S[(k + 1) + j * SLD];
-            }
-            if (k <= r) acc0 += S[r + k * SLD] * S[k + j * SLD];
-        }
-        __syncthreads();
-        if (r > j) S[r + j * SLD] = -(acc0 + acc1) * ajj;
-        if (r == j) S[j + j * SLD] = ajj;
-        __syncthreads();
-    }
-    for (int c = 0; c < NB; ++c) Li[r + (int64_t)c * ldi] = S[r + c * SLD];
-}
 
 int launch_base(gpk_handle h, double* A, int64_t lda, double* Li, int64_t ldi, int col_offset, int mode, int batch,
                 int64_t strideA, int64_t strideLi) {
-    const size_t smem = (size_t)NB * SLD * sizeof(double);
-    if (!(h->func_cfg & (1u << 8))) {
-        GPK_CUDA(h, cudaFuncSetAttribute(potf2_trti2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->func_cfg |= (1u << 8);
-    }
-    potf2_trti2_kernel<<<batch, NB, smem, h->stream>>>(A, lda, Li, ldi, h->d_info, col_offset, mode, strideA, strideLi);
-    GPK_LAUNCH_CHECK(h);
-    return GPK_OK;
+    return gpk_base_potrf_trtri(h, A, lda, Li, ldi, col_offset, mode, batch, strideA, strideLi);
 }
 
-// Li21 = -Li22 * (L21 * Li11)   for the split [n1 | n2] of an (n1+n2) block
-int inverse_offdiag(gpk_handle h, const double* L21, int64_t ldl, double* Li, int64_t ldi, double* T, int n1, int n2) {
-    const double* Li11 = Li;
-    double* Li21 = Li + n1;
-    const double* Li22 = Li + n1 + (int64_t)n1 * ldi;
-    // T (n2 x n1, ld n2) = L21 * Li11 :  C(m,c) = sum_{k>=c} L21(m,k) Li11(k,c)
+struct StreamSwap {  // run the enclosed launches on another stream of the same handle
+    gpk_handle h; cudaStream_t saved;
+    StreamSwap(gpk_handle h_, cudaStream_t s) : h(h_), saved(h_->stream) { h->stream = s; }
+    ~StreamSwap() { h->stream = saved; }
+};
+
+int side_min() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPK_SIDE_MIN"); v = e ? atoi(e) : 256; }
+    return v;
+}
+
+// T (n2 x n1, ld n2) = L21 * Li11 :  C(m,c) = sum_{k>=c} L21(m,k) Li11(k,c)
+int gemm_T(gpk_handle h, const double* L21, int64_t ldl, const double* Li11, int64_t ldi, double* T, int n1, int n2) {
     GemmDesc g = gemm_desc();
     g.P = Li11; g.ldp = ldi; g.p_kcontig = 1;   // P(r,k) = Li11(k,r)
     g.Q = L21; g.ldq = ldl; g.q_kcontig = 0;    // Q(s,k) = L21(s,k)
     g.D = T; g.ldd = n2;
     g.R = n1; g.S = n2; g.K = n1; g.kb_r = 1;
-    int rc = gpk_gemm(h, g);
-    if (rc) return rc;
-    // Li21 (n2 x n1) = -Li22 * T :  C(m,c) = -sum_{k<=m} Li22(m,k) T(k,c)
-    g = gemm_desc();
+    return gpk_gemm(h, g);
+}
+// Li21 (n2 x n1) = -Li22 * T :  C(m,c) = -sum_{k<=m} Li22(m,k) T(k,c)
+int gemm_Li21(gpk_handle h, const double* T, const double* Li22, double* Li21, int64_t ldi, int n1, int n2) {
+    GemmDesc g = gemm_desc();
     g.P = T; g.ldp = n2; g.p_kcontig = 1;       // P(r,k) = T(k,r)
     g.Q = Li22; g.ldq = ldi; g.q_kcontig = 0;   // Q(s,k) = Li22(s,k)
     g.D = Li21; g.ldd = ldi;
@@ -141,15 +58,20 @@ int inverse_offdiag(gpk_handle h, const double* L21, int64_t ldl, double* Li, in
     return gpk_gemm(h, g);
 }
 
+// Schedule: everything on the handle's stream except T = L21 * Li11, which is not needed until the very end of the
+// node.  For nodes >= side_min() it is forked to a side stream (one per recursion depth) right after L21 exists, so it
+// fills the SMs that the latency-bound sub-tree of A22 (small GEMMs, 128-block spine) leaves idle, and is joined before
+// Li21 = -Li22 * T.  Each depth has its own T region because a node's T is live across its whole second sub-tree.
 int potrf_inv_rec(gpk_handle h, double* A, int64_t lda, double* Li, int64_t ldi, double* T, int n, int keep_L,
-                  int col_offset) {
+                  int col_offset, int depth) {
     if (n == NB) return launch_base(h, A, lda, Li, ldi, col_offset, 0, 1, 0, 0);
     const int n1 = (n / NB / 2) * NB, n2 = n - n1;
     double* A21 = A + n1;
     double* A22 = A + n1 + (int64_t)n1 * lda;
     double* Li21 = Li + n1;
     double* Li22 = Li + n1 + (int64_t)n1 * ldi;
-    int rc = potrf_inv_rec(h, A, lda, Li, ldi, T, n1, keep_L, col_offset);
+    double* Tchild = T + (size_t)n1 * n2;
+    int rc = potrf_inv_rec(h, A, lda, Li, ldi, Tchild, n1, keep_L, col_offset, depth + 1);
     if (rc) return rc;
     // L21 = A21 * Li11^t, staged in Li21's (still free) slot: C(m,c) = sum_{k<=c} A21(m,k) Li11(c,k)
     GemmDesc g = gemm_desc();
@@ -159,6 +81,21 @@ int potrf_inv_rec(gpk_handle h, double* A, int64_t lda, double* Li, int64_t ldi,
     g.R = n1; g.S = n2; g.K = n1; g.ke_r = 1; g.heavy_last = 1;
     rc = gpk_gemm(h, g);
     if (rc) return rc;
+    const bool fork = n >= side_min();
+    cudaEvent_t ev_done = nullptr;
+    if (fork) {
+        cudaStream_t side = h->side[depth % GPK_NSIDE];
+        cudaEvent_t ev_l21 = h->evpool[h->ev_next++ % GPK_NEVENTS];
+        ev_done = h->evpool[h->ev_next++ % GPK_NEVENTS];
+        GPK_CUDA(h, cudaEventRecord(ev_l21, h->stream));
+        GPK_CUDA(h, cudaStreamWaitEvent(side, ev_l21, 0));
+        {
+            StreamSwap sw(h, side);
+            rc = gemm_T(h, Li21, ldi, Li, ldi, T, n1, n2);
+        }
+        if (rc) return rc;
+        GPK_CUDA(h, cudaEventRecord(ev_done, side));
+    }
     // A22 -= L21 * L21^t (lower tiles)
     g = gemm_desc();
     g.P = Li21; g.ldp = ldi; g.Q = Li21; g.ldq = ldi;
@@ -170,11 +107,23 @@ int potrf_inv_rec(gpk_handle h, double* A, int64_t lda, double* Li, int64_t ldi,
         rc = gpk_copy2d(h, A21, lda, Li21, ldi, n2, n1);
         if (rc) return rc;
     }
-    rc = potrf_inv_rec(h, A22, lda, Li22, ldi, T, n2, keep_L, col_offset + n1);
+    rc = potrf_inv_rec(h, A22, lda, Li22, ldi, Tchild, n2, keep_L, col_offset + n1, depth + 1);
     if (rc) return rc;
-    // the L21 operand of the inverse is read from the staging slot when A was not updated; the second GEMM
-    // of inverse_offdiag overwrites that slot only after the first one has consumed it (stream order).
-    return inverse_offdiag(h, keep_L ? A21 : Li21, keep_L ? lda : ldi, Li, ldi, T, n1, n2);
+    if (fork) {
+        GPK_CUDA(h, cudaStreamWaitEvent(h->stream, ev_done, 0));
+    } else {
+        rc = gemm_T(h, Li21, ldi, Li, ldi, T, n1, n2);  // L21 is still staged in Li21's slot
+        if (rc) return rc;
+    }
+    // overwrites the staging slot; T has fully consumed it (stream order / ev_done)
+    return gemm_Li21(h, T, Li22, Li21, ldi, n1, n2);
+}
+
+// Li21 = -Li22 * (L21 * Li11)   for the split [n1 | n2] of an (n1+n2) block
+int inverse_offdiag(gpk_handle h, const double* L21, int64_t ldl, double* Li, int64_t ldi, double* T, int n1, int n2) {
+    int rc = gemm_T(h, L21, ldl, Li, ldi, T, n1, n2);
+    if (rc) return rc;
+    return gemm_Li21(h, T, Li + n1 + (int64_t)n1 * ldi, Li + n1, ldi, n1, n2);
 }
 
 int trtri_rec(gpk_handle h, const double* L, int64_t ldl, double* Li, int64_t ldi, double* T, int n) {
@@ -190,13 +139,14 @@ int trtri_rec(gpk_handle h, const double* L, int64_t ldl, double* Li, int64_t ld
 }  // namespace
 
 size_t gpk_chol_scratch_doubles(int N) {
+    // sum over recursion depths of n1*n2 <= (N/2+64)^2 * (1 + 1/4 + 1/16 + ...) plus slack for uneven splits
     const size_t half = (size_t)(N / 2 + NB);
-    return half * half;
+    return half * half * 3 / 2 + (size_t)N * NB;
 }
 
 int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int col_offset) {
     GPK_CUDA(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
-    return potrf_inv_rec(h, A, N, Li, N, T, N, keep_L, col_offset);
+    return potrf_inv_rec(h, A, N, Li, N, T, N, keep_L, col_offset, 0);
 }
 
 int gpk_trtri_lower(gpk_handle h, const double* L, double* Li, double* T, int N) {

@@ -14,14 +14,13 @@
 // reads of a half-warp (4 k x 4 rows) hit 16 distinct bank pairs.
 #include "gpk_internal.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
-constexpr int TR = 128, TS = 128, TK = 16, STAGES = 4, NTHREADS = 256;
-constexpr int LDR = TR + 4;  // row stride (doubles) of a [k][x] stage   (x-contiguous source)
+constexpr int TK = 16, STAGES = 4;
 constexpr int LDK = TK + 4;  // row stride (doubles) of a [x][k] stage   (k-contiguous source)
-constexpr int STAGE_DOUBLES = (TR * LDK > TK * LDR) ? TR * LDK : TK * LDR;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * 2 * STAGE_DOUBLES * sizeof(double);
-constexpr int GROUP_S = 8;  // raster: blocks walk bands of 8 s-tiles so a wave shares operand panels in L2
+constexpr int GROUP_S = 8;   // raster: blocks walk bands of 8 s-tiles so a wave shares operand panels in L2
 
 __device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -38,28 +37,49 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
         : "d"(a), "d"(b));
 }
 
-// stage a 128 (x) by 16 (k) operand tile
-template <bool KC>
+// Tile configuration: WR x WS warps, each owning a (BI*8) x (BJ*8) sub-tile.
+//   Big  : 2 x 4 warps, 8 x 4 blocks -> 128 x 128 CTA tile, 256 threads, 1 CTA/SM   (throughput)
+//   Small: 2 x 2 warps, 4 x 4 blocks ->  64 x  64 CTA tile, 128 threads, 2 CTAs/SM  (few-tile problems: spreads a
+//          128-tile over 4 SMs; one SM can only retire 0.25 TFLOP/s of FP64)
+template <int WR_, int WS_, int BI_, int BJ_>
+struct TileCfg {
+    static constexpr int WR = WR_, WS = WS_, BI = BI_, BJ = BJ_;
+    static constexpr int TR = WR * BI * 8, TS = WS * BJ * 8, NT = 32 * WR * WS;
+    static constexpr int LDRP = TR + 4, LDRQ = TS + 4;  // row stride of a [k][x] stage (x-contiguous source), %16 == 4
+    static constexpr int P_STAGE = (TR * LDK > TK * LDRP) ? TR * LDK : TK * LDRP;
+    static constexpr int Q_STAGE = (TS * LDK > TK * LDRQ) ? TS * LDK : TK * LDRQ;
+    static constexpr size_t SMEM = (size_t)STAGES * (P_STAGE + Q_STAGE) * sizeof(double);
+    static constexpr int MIN_BLOCKS = (NT >= 256) ? 1 : 2;
+};
+using BigTile = TileCfg<2, 4, 8, 4>;
+using SmallTile = TileCfg<2, 2, 4, 4>;
+
+// stage a TX (x) by 16 (k) operand tile
+template <bool KC, int TX, int NT>
 __device__ __forceinline__ void load_tile(double* st, const double* g, int64_t ld, int x0, int k0, int tid) {
+    constexpr int PER_THREAD = TX * TK / 2 / NT;
+    constexpr int LDX = TX + 4;
     if (!KC) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int c = tid + i * NTHREADS;
-            int k = c >> 6, x = (c & 63) * 2;
-            cp_async16(st + k * LDR + x, g + (int64_t)(k0 + k) * ld + (x0 + x));
+        for (int i = 0; i < PER_THREAD; ++i) {
+            int c = tid + i * NT;
+            int k = c / (TX / 2), x = (c % (TX / 2)) * 2;
+            cp_async16(st + k * LDX + x, g + (int64_t)(k0 + k) * ld + (x0 + x));
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int c = tid + i * NTHREADS;
+        for (int i = 0; i < PER_THREAD; ++i) {
+            int c = tid + i * NT;
             int x = c >> 3, k = (c & 7) * 2;
             cp_async16(st + x * LDK + k, g + (int64_t)(x0 + x) * ld + (k0 + k));
         }
     }
 }
 
-template <bool PK, bool QK>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_dmma_kernel(const GemmDesc g) {
+template <bool PK, bool QK, class Cfg>
+__global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_BLOCKS) gemm_f64_dmma_kernel(const GemmDesc g) {
+    constexpr int TR = Cfg::TR, TS = Cfg::TS, NT = Cfg::NT, BI = Cfg::BI, BJ = Cfg::BJ;
+    constexpr int LDRP = Cfg::LDRP, LDRQ = Cfg::LDRQ;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int tilesS = g.S / TS, tilesR = g.R / TR;
@@ -70,8 +90,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_dmma_kernel(const GemmDe
     const int gs = min(GROUP_S, tilesS - first_s);
     const int within = bid - group * GROUP_S * tilesR;
     const int tr = within / gs, ts = first_s + within % gs;
-    if (g.tri_out && ts < tr) return;
     const int r0 = tr * TR, s0 = ts * TS;
+    if (g.tri_out && s0 + TS <= r0) return;
     int kbeg = 0, kend = g.K;
     if (g.kb_r) kbeg = max(kbeg, r0);
     if (g.kb_s) kbeg = max(kbeg, s0);
@@ -86,23 +106,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_dmma_kernel(const GemmDe
     const double* Cin = g.Cin ? g.Cin + b * g.strideC : nullptr;
 
     double* Ps = smem;
-    double* Qs = smem + STAGES * STAGE_DOUBLES;
+    double* Qs = smem + STAGES * Cfg::P_STAGE;
 
     const int warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
-    const int wr0 = (warp >> 2) * 64, ws0 = (warp & 3) * 32;
+    const int wr0 = (warp / Cfg::WS) * (BI * 8), ws0 = (warp % Cfg::WS) * (BJ * 8);
 
-    double acc[8][4][2];
+    double acc[BI][BJ][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < BI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < BJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nk) {
-            load_tile<PK>(Ps + s * STAGE_DOUBLES, P, g.ldp, r0, kbeg + s * TK, tid);
-            load_tile<QK>(Qs + s * STAGE_DOUBLES, Q, g.ldq, s0, kbeg + s * TK, tid);
+            load_tile<PK, TR, NT>(Ps + s * Cfg::P_STAGE, P, g.ldp, r0, kbeg + s * TK, tid);
+            load_tile<QK, TS, NT>(Qs + s * Cfg::Q_STAGE, Q, g.ldq, s0, kbeg + s * TK, tid);
         }
         cp_async_commit();
     }
@@ -114,36 +134,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_dmma_kernel(const GemmDe
             const int nx = kc + STAGES - 1;
             if (nx < nk) {
                 const int st = nx % STAGES;
-                load_tile<PK>(Ps + st * STAGE_DOUBLES, P, g.ldp, r0, kbeg + nx * TK, tid);
-                load_tile<QK>(Qs + st * STAGE_DOUBLES, Q, g.ldq, s0, kbeg + nx * TK, tid);
+                load_tile<PK, TR, NT>(Ps + st * Cfg::P_STAGE, P, g.ldp, r0, kbeg + nx * TK, tid);
+                load_tile<QK, TS, NT>(Qs + st * Cfg::Q_STAGE, Q, g.ldq, s0, kbeg + nx * TK, tid);
             }
             cp_async_commit();
         }
-        const double* ps = Ps + (kc % STAGES) * STAGE_DOUBLES;
-        const double* qs = Qs + (kc % STAGES) * STAGE_DOUBLES;
-        const double* pf = PK ? ps + (wr0 + gid) * LDK + tig : ps + tig * LDR + wr0 + gid;
-        const double* qf = QK ? qs + (ws0 + gid) * LDK + tig : qs + tig * LDR + ws0 + gid;
+        const double* ps = Ps + (kc % STAGES) * Cfg::P_STAGE;
+        const double* qs = Qs + (kc % STAGES) * Cfg::Q_STAGE;
+        const double* pf = PK ? ps + (wr0 + gid) * LDK + tig : ps + tig * LDRP + wr0 + gid;
+        const double* qf = QK ? qs + (ws0 + gid) * LDK + tig : qs + tig * LDRQ + ws0 + gid;
 #pragma unroll
         for (int kk = 0; kk < TK; kk += 4) {
-            double a[8], bb[4];
+            double a[BI], bb[BJ];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = PK ? pf[i * 8 * LDK + kk] : pf[kk * LDR + i * 8];
+            for (int i = 0; i < BI; ++i) a[i] = PK ? pf[i * 8 * LDK + kk] : pf[kk * LDRP + i * 8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bb[j] = QK ? qf[j * 8 * LDK + kk] : qf[kk * LDR + j * 8];
+            for (int j = 0; j < BJ; ++j) bb[j] = QK ? qf[j * 8 * LDK + kk] : qf[kk * LDRQ + j * 8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < BI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+                for (int j = 0; j < BJ; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
         }
     }
     cp_async_wait<0>();
 
     const double alpha = g.alpha, beta = g.beta;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < BI; ++i) {
         const int64_t r = r0 + wr0 + 8 * i + gid;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < BJ; ++j) {
             const int s = s0 + ws0 + 8 * j + 2 * tig;
             double2 v = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
             if (Cin != nullptr) {
@@ -156,27 +176,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_dmma_kernel(const GemmDe
     }
 }
 
-template <bool PK, bool QK>
-int launch(gpk_handle h, const GemmDesc& g) {
-    const unsigned bit = 1u << ((PK ? 2 : 0) + (QK ? 1 : 0));
+template <bool PK, bool QK, class Cfg>
+int launch(gpk_handle h, const GemmDesc& g, int cfg_id) {
+    const unsigned bit = 1u << (16 + cfg_id * 4 + (PK ? 2 : 0) + (QK ? 1 : 0));
     if (!(h->func_cfg & bit)) {
-        GPK_CUDA(h, cudaFuncSetAttribute(gemm_f64_dmma_kernel<PK, QK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SMEM_BYTES));
+        GPK_CUDA(h, cudaFuncSetAttribute(gemm_f64_dmma_kernel<PK, QK, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM));
         h->func_cfg |= bit;
     }
-    dim3 grid((unsigned)((g.R / TR) * (g.S / TS)), (unsigned)g.batch);
-    gemm_f64_dmma_kernel<PK, QK><<<grid, NTHREADS, SMEM_BYTES, h->stream>>>(g);
+    dim3 grid((unsigned)((g.R / Cfg::TR) * (g.S / Cfg::TS)), (unsigned)g.batch);
+    gemm_f64_dmma_kernel<PK, QK, Cfg><<<grid, Cfg::NT, Cfg::SMEM, h->stream>>>(g);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
+}
+
+template <class Cfg>
+int dispatch(gpk_handle h, const GemmDesc& g, int cfg_id) {
+    if (g.p_kcontig) return g.q_kcontig ? launch<true, true, Cfg>(h, g, cfg_id) : launch<true, false, Cfg>(h, g, cfg_id);
+    return g.q_kcontig ? launch<false, true, Cfg>(h, g, cfg_id) : launch<false, false, Cfg>(h, g, cfg_id);
+}
+
+int small_tile_threshold() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPK_SMALL_TILE_THRESHOLD");
+        v = e ? atoi(e) : 296;  // fewer 128-tiles than ~2 waves of 148 SMs -> 64x64 tiles
+    }
+    return v;
 }
 
 }  // namespace
 
 int gpk_gemm(gpk_handle h, const GemmDesc& g) {
     if (g.R <= 0 || g.S <= 0 || g.batch <= 0) return GPK_OK;
-    if (g.R % TR || g.S % TS || g.K % TK || (g.ldp & 1) || (g.ldq & 1) || (g.ldd & 1) ||
+    if (g.R % 128 || g.S % 128 || g.K % TK || (g.ldp & 1) || (g.ldq & 1) || (g.ldd & 1) ||
         ((uintptr_t)g.P & 15) || ((uintptr_t)g.Q & 15) || ((uintptr_t)g.D & 15) || (g.Cin && (((uintptr_t)g.Cin & 15) || (g.ldc & 1))))
         return gpk_set_error(h, GPK_EINVAL, "gpk_gemm: unaligned problem R=%d S=%d K=%d", g.R, g.S, g.K);
-    if (g.p_kcontig) return g.q_kcontig ? launch<true, true>(h, g) : launch<true, false>(h, g);
-    return g.q_kcontig ? launch<false, true>(h, g) : launch<false, false>(h, g);
+    int64_t tiles = (int64_t)(g.R / 128) * (g.S / 128) * g.batch;
+    if (g.tri_out) tiles = (tiles + g.batch * (g.R / 128)) / 2;
+    if (tiles < small_tile_threshold()) return dispatch<SmallTile>(h, g, 1);
+    return dispatch<BigTile>(h, g, 0);
 }

@@ -7,12 +7,17 @@
 
 #include "../../include/gpk.h"
 
-#define GPK_TILE 128  // every internal matrix dimension / leading dimension is a multiple of this
+#define GPK_TILE 128
+#define GPK_NSIDE 4      // side streams (one per recursion depth, cyclic)
+#define GPK_NEVENTS 256  // fork/join event pool (cyclic)  // every internal matrix dimension / leading dimension is a multiple of this
 
 struct gpk_handle_s {
     int device;
     cudaStream_t stream;
     bool own_stream;
+    cudaStream_t side[GPK_NSIDE];
+    cudaEvent_t evpool[GPK_NEVENTS];
+    unsigned ev_next;
     // grow-only device arenas (A: factor / K^-1, B: L^-1, T: GEMM scratch, misc: small vectors)
     void* arena[8];
     size_t arena_bytes[8];
@@ -110,6 +115,9 @@ int gpk_cov_deriv(gpk_handle h, int param_num, const double* dX, int n, int64_t 
 // diagonal 128-blocks are valid), Li = L^-1 (N x N, ld N, lower; upper parts of diagonal blocks zeroed;
 // blocks above the diagonal untouched).  T: scratch of at least gpk_chol_scratch_doubles(N).
 // ---------------------------------------------------------------------------------------------
+// base case (gpk_base.cu): batch of 128x128 blocks; mode 0 = factor + invert, mode 1 = invert a given lower factor
+int gpk_base_potrf_trtri(gpk_handle h, double* A, int64_t lda, double* Li, int64_t ldi, int col_offset, int mode, int batch,
+                         int64_t strideA, int64_t strideLi);
 size_t gpk_chol_scratch_doubles(int N);
 int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int col_offset);
 // L^-1 for a given lower-triangular L (N x N padded, ld N)
