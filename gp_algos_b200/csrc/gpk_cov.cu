@@ -30,6 +30,8 @@ struct CovArgs {
     const double* X2; int64_t ldx2; int n;  // column points
     double* K; int64_t ldk;
     int mp, np;  // padded extents written (>= m, n)
+    int64_t strideX1, strideX2, strideK;  // per-problem strides (blockIdx.z)
+    const ProblemParams* pp;               // device array of per-problem hyper-parameters, or nullptr -> cp
     CovParams cp;
 };
 
@@ -43,7 +45,12 @@ __device__ __forceinline__ void store2(double* p, double a, double b, bool ok0, 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) cov_se_ard_kernel(const CovArgs a) {
+__global__ void __launch_bounds__(256) cov_se_ard_kernel(const CovArgs a0) {
+    // per-problem view (blockIdx.z); hyper-parameters by value (single problem) or from the device array (batched)
+    struct View { const double* X1; const double* X2; double* K; int64_t ldx1, ldx2, ldk; int m, n, mp, np; const CovParams& cp; };
+    const int64_t bz = blockIdx.z;
+    const View a = {a0.X1 + bz * a0.strideX1, a0.X2 + bz * a0.strideX2, a0.K + bz * a0.strideK, a0.ldx1, a0.ldx2, a0.ldk,
+                    a0.m, a0.n, a0.mp, a0.np, a0.pp ? a0.pp[bz].cp : a0.cp};
     __shared__ double xi[DC][CT];
     __shared__ double xj[DC][CT];
     __shared__ double tbuf[(MODE == MODE_SYM_FULL) ? CT * TLD : 1];
@@ -147,6 +154,20 @@ __global__ void cov_deriv_kernel(int param_num, const double* X, int n, int64_t 
 
 }  // namespace
 
+int gpk_make_problem_params(gpk_handle h, const double* theta, int D, int has_sigma_noise, double sigma_noise, ProblemParams* out) {
+    int rc = gpk_make_cov_params(h, theta, D, has_sigma_noise, sigma_noise, &out->cp);
+    if (rc) return rc;
+    const double sf = theta[0], sn = theta[D + 1];
+    memset(out->gscale, 0, sizeof(out->gscale));
+    out->gscale[0] = sf;                                          // 1/2 * 2 sf
+    for (int d = 0; d < D; ++d) {
+        const double l = theta[1 + d];
+        out->gscale[1 + d] = 0.5 * (sf * sf) / (l * l * l);       // 1/2 * sf^2 / l_d^3
+    }
+    out->gscale[D + 1] = sn;                                      // 1/2 * 2 sn
+    return GPK_OK;
+}
+
 int gpk_make_cov_params(gpk_handle h, const double* theta, int D, int has_sigma_noise, double sigma_noise, CovParams* out) {
     if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
     memset(out, 0, sizeof(*out));
@@ -162,29 +183,34 @@ int gpk_cov_sym_full(gpk_handle h, const double* dX, int n, int64_t ldx, const C
     if (n <= 0) return GPK_OK;
     CovArgs a;
     a.X1 = dX; a.ldx1 = ldx; a.m = n; a.X2 = dX; a.ldx2 = ldx; a.n = n; a.K = dK; a.ldk = ldk; a.mp = n; a.np = n; a.cp = cp;
+    a.strideX1 = a.strideX2 = a.strideK = 0; a.pp = nullptr;
     const int t = (n + CT - 1) / CT;
     cov_se_ard_kernel<MODE_SYM_FULL><<<dim3(t, t), 256, 0, h->stream>>>(a);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }
 
-int gpk_cov_sym_lower_padded(gpk_handle h, const double* dX, int n, int64_t ldx, const CovParams& cp, double* dK, int N) {
+int gpk_cov_sym_lower_padded(gpk_handle h, const double* dX, int n, int64_t ldx, const CovParams& cp, double* dK, int N,
+                             int batch, int64_t strideX, const ProblemParams* pp_dev) {
     CovArgs a;
     a.X1 = dX; a.ldx1 = ldx; a.m = n; a.X2 = dX; a.ldx2 = ldx; a.n = n; a.K = dK; a.ldk = N; a.mp = N; a.np = N; a.cp = cp;
+    a.strideX1 = a.strideX2 = strideX; a.strideK = (int64_t)N * N; a.pp = pp_dev;
     const int t = N / CT;
-    cov_se_ard_kernel<MODE_SYM_LOWER_PAD><<<dim3(t, t), 256, 0, h->stream>>>(a);
+    cov_se_ard_kernel<MODE_SYM_LOWER_PAD><<<dim3(t, t, batch), 256, 0, h->stream>>>(a);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }
 
 int gpk_cov_cross(gpk_handle h, const double* dX1, int m, int64_t ldx1, const double* dX2, int n, int64_t ldx2,
-                  const CovParams& cp, double* dK, int64_t ldk, int mp, int np) {
+                  const CovParams& cp, double* dK, int64_t ldk, int mp, int np, int batch, int64_t strideX1, int64_t strideX2,
+                  int64_t strideK, const ProblemParams* pp_dev) {
     if (mp < m) mp = m;
     if (np < n) np = n;
     if (mp <= 0 || np <= 0) return GPK_OK;
     CovArgs a;
     a.X1 = dX1; a.ldx1 = ldx1; a.m = m; a.X2 = dX2; a.ldx2 = ldx2; a.n = n; a.K = dK; a.ldk = ldk; a.mp = mp; a.np = np; a.cp = cp;
-    cov_se_ard_kernel<MODE_CROSS><<<dim3((mp + CT - 1) / CT, (np + CT - 1) / CT), 256, 0, h->stream>>>(a);
+    a.strideX1 = strideX1; a.strideX2 = strideX2; a.strideK = strideK; a.pp = pp_dev;
+    cov_se_ard_kernel<MODE_CROSS><<<dim3((mp + CT - 1) / CT, (np + CT - 1) / CT, batch), 256, 0, h->stream>>>(a);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }

@@ -1,0 +1,499 @@
+// gpk_gp.cu -- C ABI (include/gpk.h), part 2: the fused GpPredictor pipelines
+//   gpk_gp_fit            gp/regression/GpPredictor.scala:104-124 + :144-149
+//   gpk_gp_nll_grad       gp/regression/GpPredictor.scala:60-80
+//   gpk_gp_model_* / gpk_gp_predict   GpPredictor.scala:24-58 and the GP-UKF call pattern (GPUnscentedKalmanFilter.scala:77-147)
+//   *_batched             B independent GPs of one shape per call (MLE restarts, one GP per state dimension)
+// One code path serves single and batched problems: every kernel below takes a batch count, so B problems of size n
+// cost the same number of launches as one.  K, L, L^-1, K^-1 never leave the device.
+#include "gpk_internal.cuh"
+
+#include <stdlib.h>
+
+#include <new>
+
+namespace {
+
+#define ARENA_OR_FAIL(ptr, type, h, which, bytes)           \
+    type ptr = (type)gpk_arena((h), (which), (bytes));      \
+    if (!ptr) return GPK_ENOMEM
+
+size_t batch_budget_bytes() {
+    static size_t v = 0;
+    if (!v) {
+        const char* e = getenv("GPK_BATCH_GB");
+        v = (size_t)((e ? atof(e) : 48.0) * (1ull << 30));
+    }
+    return v;
+}
+
+// Per-problem working set of the fused pipelines.
+struct Work {
+    int N, B;          // padded size, problems resident at once
+    double *A, *Li, *T, *ypad, *z, *alpha, *scratch;
+    size_t sT, sScratch;  // per-problem strides (doubles) of T and scratch
+    ProblemParams* pp_dev;
+    int* info_dev;
+};
+
+size_t per_problem_doubles(int N, int D, size_t* sT, size_t* sScr) {
+    *sT = gpk_chol_scratch_doubles(N);
+    const size_t trmv = (size_t)(N / 1024 + 1) * N;
+    const size_t grad = gpk_grad_scratch_doubles(N, D);
+    *sScr = trmv > grad ? trmv : grad;
+    return (size_t)2 * N * N + *sT + (size_t)3 * N + *sScr;
+}
+
+int make_work(gpk_handle h, int n, int D, int Bwant, Work* w) {
+    const int N = gpk_pad(n);
+    size_t sT, sScr;
+    const size_t per = per_problem_doubles(N, D, &sT, &sScr) * sizeof(double);
+    int B = Bwant;
+    if ((size_t)B * per > batch_budget_bytes()) B = (int)(batch_budget_bytes() / per);
+    if (B < 1) B = 1;
+    w->N = N; w->B = B; w->sT = sT; w->sScratch = sScr;
+    w->A = (double*)gpk_arena(h, ARENA_A, (size_t)B * N * N * sizeof(double));
+    w->Li = (double*)gpk_arena(h, ARENA_B, (size_t)B * N * N * sizeof(double));
+    w->T = (double*)gpk_arena(h, ARENA_T, (size_t)B * sT * sizeof(double));
+    double* m = (double*)gpk_arena(h, ARENA_MISC, (size_t)B * ((size_t)3 * N + sScr) * sizeof(double));
+    w->pp_dev = (ProblemParams*)gpk_arena(h, ARENA_PP, (size_t)B * sizeof(ProblemParams));
+    w->info_dev = (int*)gpk_arena(h, ARENA_INFO, (size_t)B * sizeof(int));
+    if (!w->A || !w->Li || !w->T || !m || !w->pp_dev || !w->info_dev) return GPK_ENOMEM;
+    w->ypad = m;
+    w->z = m + (size_t)B * N;
+    w->alpha = m + (size_t)2 * B * N;
+    w->scratch = m + (size_t)3 * B * N;
+    return GPK_OK;
+}
+
+// host staging of per-problem hyper-parameters; returns the by-value params of problem 0 in *first
+int stage_params(gpk_handle h, const double* thetas, int D, int has_s, double s, int B, ProblemParams* dev, ProblemParams* first) {
+    const size_t bytes = (size_t)B * sizeof(ProblemParams);
+    if (h->pp_host_bytes < bytes) {
+        free(h->pp_host);
+        h->pp_host = malloc(bytes);
+        h->pp_host_bytes = h->pp_host ? bytes : 0;
+        if (!h->pp_host) return gpk_set_error(h, GPK_ENOMEM, "host allocation failed");
+    }
+    ProblemParams* hp = (ProblemParams*)h->pp_host;
+    for (int b = 0; b < B; ++b) {
+        int rc = gpk_make_problem_params(h, thetas + (size_t)b * (D + 2), D, has_s, s, &hp[b]);
+        if (rc) return rc;
+    }
+    *first = hp[0];
+    if (B > 1) {
+        // pageable source: the runtime stages the bytes before returning, so pp_host may be reused by the next call
+        GPK_CUDA(h, cudaMemcpyAsync(dev, hp, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    return GPK_OK;
+}
+
+// K -> L^-1 (and L when keep_L), alpha, ll for `B` resident problems.  X, y on the device.
+int fit_core(gpk_handle h, const Work& w, int B, const double* dX, int n, int D, int64_t ldx, int64_t strideX, const double* dy,
+             const ProblemParams& pp0, int keep_L, double* Li, double* alpha, double* ll_dev, int64_t ll_stride, int* info_dev) {
+    const ProblemParams* ppd = (B > 1) ? w.pp_dev : nullptr;
+    int rc = gpk_cov_sym_lower_padded(h, dX, n, ldx, pp0.cp, w.A, w.N, B, strideX, ppd);
+    if (rc) return rc;
+    rc = gpk_potrf_inv(h, w.A, Li, w.T, w.N, keep_L, info_dev, B);
+    if (rc) return rc;
+    rc = gpk_pad_vector(h, w.ypad, w.N, dy, n, B);
+    if (rc) return rc;
+    rc = gpk_trmv_lower(h, Li, w.N, w.ypad, w.z, w.scratch, B);       // z = L^-1 y      (GpPredictor.scala:121)
+    if (rc) return rc;
+    rc = gpk_trmv_lower_t(h, Li, w.N, w.z, alpha, B);                  // alpha = L^-t z  (GpPredictor.scala:122)
+    if (rc) return rc;
+    return gpk_loglik(h, w.A, w.N, n, w.ypad, alpha, ll_dev, B, ll_stride);  // GpPredictor.scala:144-149
+}
+
+int nll_grad_core(gpk_handle h, int B, const double* dX, int n, int D, int64_t ldx, int64_t strideX, const double* dy,
+                  const double* thetas, int has_s, double s, int nparams, double* out_dev, int* info_dev) {
+    Work w;
+    int rc = make_work(h, n, D, B, &w);
+    if (rc) return rc;
+    const int64_t so = nparams + 1;
+    for (int b0 = 0; b0 < B; b0 += w.B) {
+        const int bc = (B - b0 < w.B) ? B - b0 : w.B;
+        ProblemParams pp0;
+        rc = stage_params(h, thetas + (size_t)b0 * (D + 2), D, has_s, s, bc, w.pp_dev, &pp0);
+        if (rc) return rc;
+        const double* X = dX + b0 * strideX;
+        int* info = info_dev ? info_dev + b0 : (B == 1 ? h->d_info : w.info_dev);
+        rc = fit_core(h, w, bc, X, n, D, ldx, strideX, dy + (size_t)b0 * n, pp0, 0, w.Li, w.alpha, out_dev + b0 * so, so, info);
+        if (rc) return rc;
+        if (nparams > 0) {
+            rc = gpk_lauum_lower(h, w.Li, w.A, w.N, bc);  // K^-1 = L^-t L^-1 (GpPredictor.scala:67), lower tiles, into A
+            if (rc) return rc;
+            rc = gpk_grad_trace(h, w.A, w.N, X, n, ldx, w.alpha, pp0, nparams, out_dev + b0 * so + 1, w.scratch, bc, strideX,
+                                bc > 1 ? w.pp_dev : nullptr, so);
+            if (rc) return rc;
+        }
+    }
+    return GPK_OK;
+}
+
+}  // namespace
+
+struct gpk_model_s {
+    int n, N, D;
+    double* X;      // n x D, ld n
+    double* Li;     // N x N
+    double* alpha;  // N
+    double theta[GPK_MAX_D + 2];
+    ProblemParams pp;
+};
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------
+// log marginal likelihood + gradient
+// ------------------------------------------------------------------------------------------------
+int gpk_gp_nll_grad_dev(gpk_handle h, const double* dX, int n, int D, int64_t ldx, const double* dy, const double* theta,
+                        int has_s, double s, int nparams, double* out_dev, int* info_dev) {
+    if (!h || n <= 0 || ldx < n) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_nll_grad: bad dimensions");
+    if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
+    if (nparams < 0 || nparams > D + 2) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, D + 2);
+    return nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev);
+}
+
+int gpk_gp_nll_grad(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y, const double* theta,
+                    int has_s, double s, int nparams, double* ll, double* grad) {
+    if (!h || n <= 0 || ldx < n) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_nll_grad: bad dimensions (require rows == targets)");
+    if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    ARENA_OR_FAIL(dX, double*, h, ARENA_X, ((size_t)n * D + n + 256) * sizeof(double));
+    double* dy = dX + (size_t)n * D;
+    double* dout = dy + n;
+    int rc = gpk_upload_matrix(h, dX, X, n, D, ldx);
+    if (rc) return rc;
+    GPK_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = gpk_gp_nll_grad_dev(h, dX, n, D, n, dy, theta, has_s, s, nparams, dout, nullptr);
+    if (rc) return rc;
+    GPK_CUDA(h, cudaMemcpyAsync(h->h_pinned, dout, (size_t)(nparams + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    rc = gpk_finish_info(h);
+    if (rc) return rc;
+    *ll = h->h_pinned[0];
+    for (int p = 0; p < nparams; ++p) grad[p] = h->h_pinned[1 + p];
+    return GPK_OK;
+}
+
+int gpk_gp_nll_grad_batched_dev(gpk_handle h, int B, const double* dX, int n, int D, int64_t ldx, int64_t strideX,
+                                const double* dy, const double* thetas, int has_s, double s, int nparams, double* out_dev,
+                                int* info_dev) {
+    if (!h || B <= 0 || n <= 0 || ldx < n || !info_dev) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_nll_grad_batched: bad arguments");
+    if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
+    if (nparams < 0 || nparams > D + 2) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, D + 2);
+    return nll_grad_core(h, B, dX, n, D, ldx, strideX, dy, thetas, has_s, s, nparams, out_dev, info_dev);
+}
+
+int gpk_gp_nll_grad_batched(gpk_handle h, int B, const double* X, int n, int D, int64_t ldx, int64_t strideX, const double* y,
+                            const double* thetas, int has_s, double s, int nparams, double* ll, double* grad, int* info) {
+    if (!h || B <= 0 || n <= 0 || ldx < n) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_nll_grad_batched: bad arguments");
+    if (strideX != 0 && strideX < (int64_t)ldx * (D - 1) + n)
+        return gpk_set_error(h, GPK_EINVAL, "gpk_gp_nll_grad_batched: strideX overlaps consecutive problems");
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    const int nx = strideX ? B : 1;
+    const size_t so = (size_t)nparams + 1;
+    ARENA_OR_FAIL(dX, double*, h, ARENA_X, ((size_t)nx * n * D + (size_t)B * n + B * so + 256) * sizeof(double) + (size_t)B * sizeof(int));
+    double* dy = dX + (size_t)nx * n * D;
+    double* dout = dy + (size_t)B * n;
+    int* dinfo = (int*)(dout + B * so);
+    int rc = GPK_OK;
+    for (int b = 0; b < nx && !rc; ++b) rc = gpk_upload_matrix(h, dX + (size_t)b * n * D, X + b * strideX, n, D, ldx);
+    if (rc) return rc;
+    GPK_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)B * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = gpk_gp_nll_grad_batched_dev(h, B, dX, n, D, n, strideX ? (int64_t)n * D : 0, dy, thetas, has_s, s, nparams, dout, dinfo);
+    if (rc) return rc;
+    double* hout = (double*)malloc(B * so * sizeof(double));
+    int* hinfo = (int*)malloc((size_t)B * sizeof(int));
+    if (!hout || !hinfo) { free(hout); free(hinfo); return gpk_set_error(h, GPK_ENOMEM, "host allocation failed"); }
+    cudaError_t e1 = cudaMemcpyAsync(hout, dout, B * so * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e2 = cudaMemcpyAsync(hinfo, dinfo, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e3 = cudaStreamSynchronize(h->stream);
+    int bad = 0;
+    if (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) {
+        for (int b = 0; b < B; ++b) {
+            ll[b] = hout[b * so];
+            for (int p = 0; p < nparams; ++p) grad[(size_t)b * nparams + p] = hout[b * so + 1 + p];
+            if (info) info[b] = hinfo[b];
+            if (hinfo[b] && !bad) { bad = 1; h->last_info = hinfo[b]; }
+        }
+    }
+    free(hout); free(hinfo);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return gpk_set_error(h, GPK_ECUDA, "result download failed");
+    if (bad) return gpk_set_error(h, GPK_ENOTPD, "at least one problem of the batch is not positive definite (see info[])");
+    return GPK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fit
+// ------------------------------------------------------------------------------------------------
+int gpk_gp_fit(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y, const double* theta, int has_s,
+               double s, double* L, int64_t ldl, double* alpha, double* ll) {
+    if (!h || n <= 0 || ldx < n || (L && ldl < n)) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_fit: bad dimensions");
+    if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    ARENA_OR_FAIL(dX, double*, h, ARENA_X, ((size_t)n * D + n + 256) * sizeof(double));
+    double* dy = dX + (size_t)n * D;
+    double* dout = dy + n;
+    int rc = gpk_upload_matrix(h, dX, X, n, D, ldx);
+    if (rc) return rc;
+    GPK_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    Work w;
+    rc = make_work(h, n, D, 1, &w);
+    if (rc) return rc;
+    ProblemParams pp;
+    rc = gpk_make_problem_params(h, theta, D, has_s, s, &pp);
+    if (rc) return rc;
+    rc = fit_core(h, w, 1, dX, n, D, n, 0, dy, pp, L != nullptr, w.Li, w.alpha, dout, 1, h->d_info);
+    if (rc) return rc;
+    GPK_CUDA(h, cudaMemcpyAsync(h->h_pinned, dout, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    rc = gpk_finish_info(h);
+    if (rc) return rc;
+    if (ll) *ll = h->h_pinned[0];
+    if (alpha) GPK_CUDA(h, cudaMemcpyAsync(alpha, w.alpha, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (L) {
+        ARENA_OR_FAIL(dOut, double*, h, ARENA_IO, (size_t)n * n * sizeof(double));
+        rc = gpk_store_lower(h, dOut, n, w.A, w.N, n);
+        if (rc) return rc;
+        rc = gpk_download_matrix(h, L, ldl, dOut, n, n);
+        if (rc) return rc;
+    }
+    return gpk_synchronize(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// resident model + prediction
+// ------------------------------------------------------------------------------------------------
+static int model_alloc(gpk_handle h, int n, int D, const double* theta, gpk_model* out) {
+    gpk_model m = new (std::nothrow) gpk_model_s();
+    if (!m) return GPK_ENOMEM;
+    memset(m, 0, sizeof(*m));
+    m->n = n; m->N = gpk_pad(n); m->D = D;
+    memcpy(m->theta, theta, sizeof(double) * (D + 2));
+    if (cudaMalloc((void**)&m->X, (size_t)n * D * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&m->Li, (size_t)m->N * m->N * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&m->alpha, (size_t)m->N * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        if (m->X) cudaFree(m->X);
+        if (m->Li) cudaFree(m->Li);
+        if (m->alpha) cudaFree(m->alpha);
+        delete m;
+        return gpk_set_error(h, GPK_ENOMEM, "model allocation failed (n=%d)", n);
+    }
+    *out = m;
+    return GPK_OK;
+}
+
+int gpk_gp_model_destroy(gpk_handle h, gpk_model m) {
+    if (!m) return GPK_OK;
+    if (h) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+    cudaFree(m->X); cudaFree(m->Li); cudaFree(m->alpha);
+    delete m;
+    return GPK_OK;
+}
+
+int gpk_gp_model_fit(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y, const double* theta,
+                     int has_s, double s, gpk_model* out, double* ll) {
+    if (!h || !out || n <= 0 || ldx < n) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_model_fit: bad dimensions");
+    if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    gpk_model m = nullptr;
+    int rc = model_alloc(h, n, D, theta, &m);
+    if (rc) return rc;
+    double* dy = (double*)gpk_arena(h, ARENA_X, ((size_t)n + 256) * sizeof(double));
+    if (!dy) rc = GPK_ENOMEM;
+    double* dout = dy + n;
+    if (!rc) rc = gpk_upload_matrix(h, m->X, X, n, D, ldx);
+    if (!rc) rc = (cudaMemcpyAsync(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream) == cudaSuccess) ? 0 : GPK_ECUDA;
+    Work w;
+    if (!rc) rc = make_work(h, n, D, 1, &w);
+    if (!rc) rc = gpk_make_problem_params(h, theta, D, has_s, s, &m->pp);
+    // factor straight into the model's resident buffers
+    if (!rc) rc = fit_core(h, w, 1, m->X, n, D, n, 0, dy, m->pp, 0, m->Li, m->alpha, dout, 1, h->d_info);
+    if (!rc) rc = (cudaMemcpyAsync(h->h_pinned, dout, sizeof(double), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess) ? 0 : GPK_ECUDA;
+    if (!rc) rc = gpk_finish_info(h);
+    if (rc) { gpk_gp_model_destroy(h, m); return rc; }
+    // predictions never include the Option sigmaNoise in the kernel (GpPredictor.scala:31,36 use newKernelFunc only)
+    m->pp.cp.extra_diag = 0.0;
+    if (ll) *ll = h->h_pinned[0];
+    *out = m;
+    return GPK_OK;
+}
+
+int gpk_gp_model_from_factor(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* L, int64_t ldl,
+                             const double* alpha, const double* theta, gpk_model* out) {
+    if (!h || !out || n <= 0 || ldx < n || ldl < n) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_model_from_factor: bad dimensions");
+    if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    gpk_model m = nullptr;
+    int rc = model_alloc(h, n, D, theta, &m);
+    if (rc) return rc;
+    const int N = m->N;
+    rc = gpk_make_problem_params(h, theta, D, 0, 0.0, &m->pp);
+    double* dIn = (double*)gpk_arena(h, ARENA_IO, (size_t)n * n * sizeof(double));
+    double* dA = (double*)gpk_arena(h, ARENA_A, (size_t)N * N * sizeof(double));
+    double* dT = (double*)gpk_arena(h, ARENA_T, gpk_chol_scratch_doubles(N) * sizeof(double));
+    if (!dIn || !dA || !dT) rc = GPK_ENOMEM;
+    if (!rc) rc = gpk_upload_matrix(h, m->X, X, n, D, ldx);
+    if (!rc) rc = gpk_upload_matrix(h, dIn, L, n, n, ldl);
+    if (!rc) rc = gpk_load_tri_padded(h, dA, N, dIn, n, n, 0);
+    if (!rc) rc = gpk_trtri_lower(h, dA, m->Li, dT, N);
+    if (!rc) rc = (cudaMemsetAsync(m->alpha, 0, (size_t)N * sizeof(double), h->stream) == cudaSuccess) ? 0 : GPK_ECUDA;
+    if (!rc) rc = (cudaMemcpyAsync(m->alpha, alpha, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream) == cudaSuccess) ? 0 : GPK_ECUDA;
+    if (!rc) rc = gpk_synchronize(h);
+    if (rc) { gpk_gp_model_destroy(h, m); return rc; }
+    *out = m;
+    return GPK_OK;
+}
+
+int gpk_gp_model_predict(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_t ldxs, int want_full_cov, double* mean,
+                         double* sigma, int64_t lds, double* V, int64_t ldv) {
+    if (!h || !m || ms <= 0 || ldxs < ms || (V && ldv < m->n) || (want_full_cov && sigma && lds < ms))
+        return gpk_set_error(h, GPK_EINVAL, "gpk_gp_model_predict: bad dimensions");
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    const int n = m->n, N = m->N, D = m->D, M = gpk_pad(ms);
+    const CovParams& cp = m->pp.cp;
+    ARENA_OR_FAIL(dXs, double*, h, ARENA_X, (size_t)ms * D * sizeof(double));
+    // KsT (N x M), V (N x M), Sig (M x M), mean (M), var (M)
+    ARENA_OR_FAIL(buf, double*, h, ARENA_IO2, ((size_t)2 * N * M + (size_t)M * M + 2 * M) * sizeof(double));
+    double* dKsT = buf;
+    double* dV = dKsT + (size_t)N * M;
+    double* dSig = dV + (size_t)N * M;
+    double* dMean = dSig + (size_t)M * M;
+    double* dVar = dMean + M;
+    int rc = gpk_upload_matrix(h, dXs, Xs, ms, D, ldxs);
+    if (rc) return rc;
+    // K*^t = k(X, X*) : N x M with zero padding (GpPredictor.scala:53, no noise)
+    rc = gpk_cov_cross(h, m->X, n, n, dXs, ms, ms, cp, dKsT, N, N, M);
+    if (rc) return rc;
+    // mean = K* alpha (GpPredictor.scala:54)
+    rc = gpk_colwise_dot(h, dKsT, N, N, ms, m->alpha, dMean, 0);
+    if (rc) return rc;
+    // V = L^-1 K*^t (GpPredictor.scala:55): C(i,c) = sum_{k<=i} Li(i,k) KsT(k,c)
+    GemmDesc g = gemm_desc();
+    g.P = dKsT; g.ldp = N; g.p_kcontig = 1;
+    g.Q = m->Li; g.ldq = N; g.q_kcontig = 0;
+    g.D = dV; g.ldd = N; g.R = M; g.S = N; g.K = N; g.ke_s = 1; g.heavy_last = 1;
+    rc = gpk_gemm(h, g);
+    if (rc) return rc;
+    if (mean) GPK_CUDA(h, cudaMemcpyAsync(mean, dMean, (size_t)ms * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (sigma) {
+        if (want_full_cov) {
+            // sigma = k(X*,X*) (+ sn^2 on the diagonal, MatrixUtils.scala:63) - V^t V   (GpPredictor.scala:56)
+            GPK_CUDA(h, cudaMemsetAsync(dSig, 0, (size_t)M * M * sizeof(double), h->stream));
+            rc = gpk_cov_sym_full(h, dXs, ms, ms, cp, dSig, M);
+            if (rc) return rc;
+            g = gemm_desc();
+            g.P = dV; g.ldp = N; g.p_kcontig = 1;
+            g.Q = dV; g.ldq = N; g.q_kcontig = 1;
+            g.D = dSig; g.ldd = M; g.Cin = dSig; g.ldc = M; g.R = M; g.S = M; g.K = N; g.alpha = -1.0; g.beta = 1.0;
+            rc = gpk_gemm(h, g);
+            if (rc) return rc;
+            GPK_CUDA(h, cudaMemcpy2DAsync(sigma, (size_t)lds * sizeof(double), dSig, (size_t)M * sizeof(double),
+                                          (size_t)ms * sizeof(double), (size_t)ms, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            rc = gpk_colwise_dot(h, dV, N, N, ms, nullptr, dVar, 1);
+            if (rc) return rc;
+            GPK_CUDA(h, cudaMemcpyAsync(sigma, dVar, (size_t)ms * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    if (V) GPK_CUDA(h, cudaMemcpy2DAsync(V, (size_t)ldv * sizeof(double), dV, (size_t)N * sizeof(double), (size_t)n * sizeof(double),
+                                         (size_t)ms, cudaMemcpyDeviceToHost, h->stream));
+    rc = gpk_synchronize(h);
+    if (rc) return rc;
+    if (sigma && !want_full_cov) {
+        const double kss = cp.sf2 + cp.sn2;  // k(x*,x*) incl. the i==j noise term
+        for (int i = 0; i < ms; ++i) sigma[i] = kss - sigma[i];
+    }
+    return GPK_OK;
+}
+
+int gpk_gp_predict(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y, const double* Xs, int ms,
+                   int64_t ldxs, const double* theta, int has_s, double s, double* mean, double* sigma, int64_t lds, double* ll) {
+    gpk_model m = nullptr;
+    int rc = gpk_gp_model_fit(h, X, n, D, ldx, y, theta, has_s, s, &m, ll);
+    if (rc) return rc;
+    rc = gpk_gp_model_predict(h, m, Xs, ms, ldxs, 1, mean, sigma, lds, nullptr, 0);
+    gpk_gp_model_destroy(h, m);
+    if (rc) return rc;
+    if (has_s && sigma)  // GpPredictor.scala:37-39: + sigmaNoise * I
+        for (int i = 0; i < ms; ++i) sigma[i + (int64_t)i * lds] += s;
+    return GPK_OK;
+}
+
+// B independent GPs: fit each (its own theta_b, y_b; X shared when strideX == 0) and evaluate the posterior mean and
+// variance at ms test rows each -- the GP-UKF sigma-point pattern (GPUnscentedKalmanFilter.scala:77-88,138-147).
+int gpk_gp_predict_batched(gpk_handle h, int B, const double* X, int n, int D, int64_t ldx, int64_t strideX, const double* y,
+                           const double* thetas, const double* Xs, int ms, int64_t ldxs, int64_t strideXs, int has_s, double s,
+                           double* mean, double* var, double* ll, int* info) {
+    if (!h || B <= 0 || n <= 0 || ms <= 0 || ldx < n || ldxs < ms) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_predict_batched: bad arguments");
+    if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    const int N = gpk_pad(n), M = gpk_pad(ms);
+    Work w;
+    int rc = make_work(h, n, D, B, &w);
+    if (rc) return rc;
+    const int Bc = w.B;
+    const int nx = strideX ? Bc : 1, nxs = strideXs ? Bc : 1;
+    ARENA_OR_FAIL(dX, double*, h, ARENA_X, ((size_t)nx * n * D + (size_t)nxs * ms * D + (size_t)Bc * n + Bc + 256) * sizeof(double));
+    double* dXs = dX + (size_t)nx * n * D;
+    double* dy = dXs + (size_t)nxs * ms * D;
+    double* dll = dy + (size_t)Bc * n;
+    ARENA_OR_FAIL(buf, double*, h, ARENA_IO2, (size_t)Bc * ((size_t)2 * N * M + 2 * M) * sizeof(double));
+    double* dKsT = buf;
+    double* dV = dKsT + (size_t)Bc * N * M;
+    double* dMean = dV + (size_t)Bc * N * M;
+    double* dVar = dMean + (size_t)Bc * M;
+    int* hinfo = (int*)malloc((size_t)B * sizeof(int));
+    if (!hinfo) return gpk_set_error(h, GPK_ENOMEM, "host allocation failed");
+    int bad = 0;
+    for (int b0 = 0; b0 < B && !rc; b0 += Bc) {
+        const int bc = (B - b0 < Bc) ? B - b0 : Bc;
+        ProblemParams pp0;
+        rc = stage_params(h, thetas + (size_t)b0 * (D + 2), D, has_s, s, bc, w.pp_dev, &pp0);
+        for (int b = 0; b < (strideX ? bc : 1) && !rc; ++b)
+            rc = gpk_upload_matrix(h, dX + (size_t)b * n * D, X + (strideX ? (b0 + b) * strideX : 0), n, D, ldx);
+        for (int b = 0; b < (strideXs ? bc : 1) && !rc; ++b)
+            rc = gpk_upload_matrix(h, dXs + (size_t)b * ms * D, Xs + (strideXs ? (b0 + b) * strideXs : 0), ms, D, ldxs);
+        if (rc) break;
+        if (cudaMemcpyAsync(dy, y + (size_t)b0 * n, (size_t)bc * n * sizeof(double), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = GPK_ECUDA; break; }
+        const int64_t sX = strideX ? (int64_t)n * D : 0, sXs = strideXs ? (int64_t)ms * D : 0;
+        rc = fit_core(h, w, bc, dX, n, D, n, sX, dy, pp0, 0, w.Li, w.alpha, dll, 1, w.info_dev);
+        if (rc) break;
+        // predictions use the kernel without the Option sigmaNoise: extra_diag does not enter cross-covariances
+        const ProblemParams* ppd = bc > 1 ? w.pp_dev : nullptr;
+        rc = gpk_cov_cross(h, dX, n, n, dXs, ms, ms, pp0.cp, dKsT, N, N, M, bc, sX, sXs, (int64_t)N * M, ppd);
+        if (rc) break;
+        rc = gpk_colwise_dot(h, dKsT, N, N, ms, w.alpha, dMean, 0, bc, (int64_t)N * M, N, M);
+        if (rc) break;
+        GemmDesc g = gemm_desc();
+        g.P = dKsT; g.ldp = N; g.p_kcontig = 1; g.strideP = (int64_t)N * M;
+        g.Q = w.Li; g.ldq = N; g.q_kcontig = 0; g.strideQ = (int64_t)N * N;
+        g.D = dV; g.ldd = N; g.strideD = (int64_t)N * M; g.batch = bc;
+        g.R = M; g.S = N; g.K = N; g.ke_s = 1; g.heavy_last = 1;
+        rc = gpk_gemm(h, g);
+        if (rc) break;
+        rc = gpk_colwise_dot(h, dV, N, N, ms, nullptr, dVar, 1, bc, (int64_t)N * M, 0, M);
+        if (rc) break;
+        cudaError_t e = cudaMemcpy2DAsync(mean + (size_t)b0 * ms, (size_t)ms * sizeof(double), dMean, (size_t)M * sizeof(double),
+                                          (size_t)ms * sizeof(double), (size_t)bc, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(var + (size_t)b0 * ms, (size_t)ms * sizeof(double), dVar, (size_t)M * sizeof(double),
+                                                    (size_t)ms * sizeof(double), (size_t)bc, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && ll) e = cudaMemcpyAsync(ll + b0, dll, (size_t)bc * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hinfo + b0, w.info_dev, (size_t)bc * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { rc = gpk_set_error(h, GPK_ECUDA, "batched predict: %s", cudaGetErrorString(e)); break; }
+        for (int b = 0; b < bc; ++b) {
+            const double* th = thetas + (size_t)(b0 + b) * (D + 2);
+            const double kss = th[0] * th[0] + th[D + 1] * th[D + 1];  // k(x*,x*) incl. the i==j noise term (MatrixUtils.scala:63)
+            for (int i = 0; i < ms; ++i) var[(size_t)(b0 + b) * ms + i] = kss - var[(size_t)(b0 + b) * ms + i];
+            if (info) info[b0 + b] = hinfo[b0 + b];
+            if (hinfo[b0 + b] && !bad) { bad = 1; h->last_info = hinfo[b0 + b]; }
+        }
+    }
+    free(hinfo);
+    if (rc) return rc;
+    if (bad) return gpk_set_error(h, GPK_ENOTPD, "at least one problem of the batch is not positive definite (see info[])");
+    return GPK_OK;
+}
+
+}  // extern "C"

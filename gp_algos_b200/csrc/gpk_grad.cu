@@ -8,6 +8,7 @@
 //   p = 1      : dk = 2 sf e                       e = exp(-r/2)
 //   2..D+1     : dk = sf^2 e (x_id - x_jd)^2 / l_d^3
 //   D+2        : dk = 2 sn [i == j]
+// Batched over independent problems through blockIdx.y.
 #include "gpk_internal.cuh"
 
 namespace {
@@ -19,7 +20,9 @@ struct GradArgs {
     const double* Kinv; int N;
     const double* X; int64_t ldx; int n;
     const double* alpha;
-    double* partial;  // [numBlocks][D + 2]
+    double* partial;  // [batch][numBlocks][D + 2]
+    int64_t strideX;
+    const ProblemParams* pp;  // device array or nullptr -> cp
     CovParams cp;
 };
 
@@ -39,7 +42,12 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 __global__ void __launch_bounds__(256) grad_trace_kernel(const GradArgs a) {
     extern __shared__ double sm[];  // xi[D][GT], xj[D][GT]
     __shared__ double red[8];
-    const int D = a.cp.D;
+    const int64_t pb = blockIdx.y;
+    const CovParams& cp = a.pp ? a.pp[pb].cp : a.cp;
+    const double* Kinv = a.Kinv + pb * (int64_t)a.N * a.N;
+    const double* X = a.X + pb * a.strideX;
+    const double* alpha = a.alpha + pb * a.N;
+    const int D = cp.D;
     double* xi = sm;
     double* xj = sm + D * GT;
     // linear block id -> lower-triangular tile (bi >= bj)
@@ -54,8 +62,8 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const GradArgs a) {
     for (int e = tid; e < D * GT; e += 256) {
         const int d = e / GT, l = e % GT;
         const int gi = i0 + l, gj = j0 + l;
-        xi[e] = (gi < a.n) ? a.X[gi + (int64_t)d * a.ldx] : 0.0;
-        xj[e] = (gj < a.n) ? a.X[gj + (int64_t)d * a.ldx] : 0.0;
+        xi[e] = (gi < a.n) ? X[gi + (int64_t)d * a.ldx] : 0.0;
+        xj[e] = (gj < a.n) ? X[gj + (int64_t)d * a.ldx] : 0.0;
     }
     __syncthreads();
 
@@ -70,7 +78,7 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const GradArgs a) {
 #pragma unroll
             for (int b = 0; b < 8; ++b) r[q][b] = 0.0;
         for (int d = 0; d < D; ++d) {
-            const double inv = a.cp.inv_ls2[d];
+            const double inv = cp.inv_ls2[d];
             const double x0 = xi[d * GT + 2 * tx], x1 = xi[d * GT + 2 * tx + 1];
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
@@ -80,12 +88,12 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const GradArgs a) {
                 r[1][b] += (f1 * inv) * f1;
             }
         }
-        const double al0 = (gi0 < a.n) ? a.alpha[gi0] : 0.0, al1 = (gi0 + 1 < a.n) ? a.alpha[gi0 + 1] : 0.0;
+        const double al0 = (gi0 < a.n) ? alpha[gi0] : 0.0, al1 = (gi0 + 1 < a.n) ? alpha[gi0 + 1] : 0.0;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const int gj = j0 + ty + 8 * b;
-            const double aj = (gj < a.n) ? a.alpha[gj] : 0.0;
-            const double2 kv = *reinterpret_cast<const double2*>(a.Kinv + gi0 + (int64_t)gj * a.N);
+            const double aj = (gj < a.n) ? alpha[gj] : 0.0;
+            const double2 kv = *reinterpret_cast<const double2*>(Kinv + gi0 + (int64_t)gj * a.N);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int gi = gi0 + q;
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const GradArgs a) {
         }
     }
 
-    double* out = a.partial + (int64_t)blockIdx.x * (D + 2);
+    double* out = a.partial + (pb * gridDim.x + blockIdx.x) * (int64_t)(D + 2);
     {   // p = 1 (signal) and p = D+2 (noise)
         double s = 0.0;
 #pragma unroll
@@ -136,13 +144,16 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const GradArgs a) {
     }
 }
 
-// g[p] = scale[p] * sum_blocks partial[block][p]   (fixed order -> deterministic)
+// g[b][p] = gscale_b[p] * sum_blocks partial[b][block][p]   (fixed order -> deterministic)
 struct GradScale { double s[GPK_MAX_D + 2]; };
 __global__ void __launch_bounds__(256) grad_finish_kernel(const double* partial, int nblocks, int np_all, int nparams,
-                                                          const GradScale scale, double* g) {
+                                                          const GradScale scale, const ProblemParams* pp, double* g,
+                                                          int64_t strideOut) {
     __shared__ double sd[256];
     const int p = blockIdx.x;
+    const int64_t pb = blockIdx.y;
     if (p >= nparams) return;
+    partial += pb * (int64_t)nblocks * np_all;
     double s = 0.0;
     for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(int64_t)b * np_all + p];
     sd[threadIdx.x] = s;
@@ -151,7 +162,7 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(const double* partial,
         if (threadIdx.x < k) sd[threadIdx.x] += sd[threadIdx.x + k];
         __syncthreads();
     }
-    if (threadIdx.x == 0) g[p] = scale.s[p] * sd[0];
+    if (threadIdx.x == 0) g[pb * strideOut + p] = (pp ? pp[pb].gscale[p] : scale.s[p]) * sd[0];
 }
 
 }  // namespace
@@ -162,28 +173,26 @@ size_t gpk_grad_scratch_doubles(int N, int D) {
 }
 
 int gpk_grad_trace(gpk_handle h, const double* Kinv, int N, const double* dX, int n, int64_t ldx, const double* alpha,
-                   const CovParams& cp, double sf, double sn, const double* ls_host, int nparams, double* g_out,
-                   double* scratch) {
-    const int D = cp.D;
+                   const ProblemParams& pp, int nparams, double* g_out, double* scratch, int batch, int64_t strideX,
+                   const ProblemParams* pp_dev, int64_t strideOut) {
+    const int D = pp.cp.D;
     if (nparams < 0 || nparams > D + 2) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, D + 2);
     if (nparams == 0) return GPK_OK;
     const int nt = (n + GT - 1) / GT;
     const int nblocks = nt * (nt + 1) / 2;
     GradArgs a;
-    a.Kinv = Kinv; a.N = N; a.X = dX; a.ldx = ldx; a.n = n; a.alpha = alpha; a.partial = scratch; a.cp = cp;
+    a.Kinv = Kinv; a.N = N; a.X = dX; a.ldx = ldx; a.n = n; a.alpha = alpha; a.partial = scratch; a.cp = pp.cp;
+    a.strideX = strideX; a.pp = pp_dev;
     const size_t smem = (size_t)2 * D * GT * sizeof(double);
     if (smem > 48 * 1024 && !(h->func_cfg & (1u << 9))) {
         GPK_CUDA(h, cudaFuncSetAttribute(grad_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->func_cfg |= (1u << 9);
     }
-    grad_trace_kernel<<<nblocks, 256, smem, h->stream>>>(a);
+    grad_trace_kernel<<<dim3(nblocks, batch), 256, smem, h->stream>>>(a);
     GPK_LAUNCH_CHECK(h);
-    // scale factors: 1/2 * {2 sf, sf^2 / l_d^3, 2 sn}
     GradScale sc;
-    sc.s[0] = sf;
-    for (int d = 0; d < D; ++d) sc.s[1 + d] = 0.5 * (sf * sf) / (ls_host[d] * ls_host[d] * ls_host[d]);
-    sc.s[D + 1] = sn;
-    grad_finish_kernel<<<nparams, 256, 0, h->stream>>>(scratch, nblocks, D + 2, nparams, sc, g_out);
+    memcpy(sc.s, pp.gscale, sizeof(sc.s));
+    grad_finish_kernel<<<dim3(nparams, batch), 256, 0, h->stream>>>(scratch, nblocks, D + 2, nparams, sc, pp_dev, g_out, strideOut);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }

@@ -19,21 +19,26 @@ struct gpk_handle_s {
     cudaEvent_t evpool[GPK_NEVENTS];
     unsigned ev_next;
     // grow-only device arenas (A: factor / K^-1, B: L^-1, T: GEMM scratch, misc: small vectors)
-    void* arena[8];
-    size_t arena_bytes[8];
+    void* arena[12];
+    size_t arena_bytes[12];
     double* h_pinned;  // 4096 doubles of pinned host scratch
     int* d_info;       // device int: first failing minor of the last factorisation
     int last_info;
     int64_t launches;
     unsigned func_cfg;  // bitmask: kernels whose dynamic-smem attribute has been set on this device
+    void* pp_host;           // host staging for per-problem hyper-parameters (batched calls)
+    size_t pp_host_bytes;
     char err[512];
 };
 
-enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7 };
+enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7, ARENA_PP = 8, ARENA_INFO = 9, GPK_NARENA = 12 };
 
 int gpk_set_error(gpk_handle h, int status, const char* fmt, ...);
 // returns device pointer to at least `bytes` bytes in arena `which` (contents undefined after growth)
 void* gpk_arena(gpk_handle h, int which, size_t bytes);
+int gpk_upload_matrix(gpk_handle h, double* dst, const double* src, int rows, int cols, int64_t ld);   // host (ld) -> device (ld = rows)
+int gpk_download_matrix(gpk_handle h, double* dst, int64_t ld, const double* src, int rows, int cols);  // device (ld = rows) -> host (ld)
+int gpk_finish_info(gpk_handle h);  // sync, read h->d_info[0], map to GPK_ENOTPD
 
 #define GPK_CUDA(h, call)                                                                         \
     do {                                                                                          \
@@ -88,7 +93,10 @@ static inline GemmDesc gemm_desc() {
 int gpk_gemm(gpk_handle h, const GemmDesc& g);
 
 // ---------------------------------------------------------------------------------------------
-// covariance (gpk_cov.cu)
+// Batching convention (C4: many independent GPs of the same shape): every internal routine takes a
+// trailing `batch` count.  Problem b uses matrix b at base + b*N*N, vector b at base + b*N, X at dX + b*strideX
+// (strideX == 0: all problems share X, the GP-UKF case), y at dy + b*n, and hyper-parameters pp_dev[b].  With
+// batch == 1 and pp_dev == nullptr the hyper-parameters travel by value in the kernel arguments.
 // ---------------------------------------------------------------------------------------------
 #define GPK_MAX_D 64
 struct CovParams {
@@ -98,14 +106,25 @@ struct CovParams {
     double extra_diag;   // Option sigmaNoise (un-squared), 0 when None
     double inv_ls2[GPK_MAX_D];  // 1/(ls*ls)
 };
+struct ProblemParams {
+    CovParams cp;
+    double gscale[GPK_MAX_D + 2];  // 1/2 * {2 sf, sf^2 / l_d^3 ..., 2 sn}: factors of the gradient trace
+};
 int gpk_make_cov_params(gpk_handle h, const double* theta, int D, int has_sigma_noise, double sigma_noise, CovParams* out);
+int gpk_make_problem_params(gpk_handle h, const double* theta, int D, int has_sigma_noise, double sigma_noise, ProblemParams* out);
+
+// ---------------------------------------------------------------------------------------------
+// covariance (gpk_cov.cu)
+// ---------------------------------------------------------------------------------------------
 // full symmetric n x n (mirrored) into K (ld ldk)
 int gpk_cov_sym_full(gpk_handle h, const double* dX, int n, int64_t ldx, const CovParams& cp, double* dK, int64_t ldk);
 // lower tiles only of the padded N x N matrix (N = gpk_pad(n)); padding = identity
-int gpk_cov_sym_lower_padded(gpk_handle h, const double* dX, int n, int64_t ldx, const CovParams& cp, double* dK, int N);
+int gpk_cov_sym_lower_padded(gpk_handle h, const double* dX, int n, int64_t ldx, const CovParams& cp, double* dK, int N,
+                             int batch = 1, int64_t strideX = 0, const ProblemParams* pp_dev = nullptr);
 // rectangular m x n, no noise; rows>=m / cols>=n up to (mp, np) are zero-filled when mp/np > m/n
 int gpk_cov_cross(gpk_handle h, const double* dX1, int m, int64_t ldx1, const double* dX2, int n, int64_t ldx2,
-                  const CovParams& cp, double* dK, int64_t ldk, int mp, int np);
+                  const CovParams& cp, double* dK, int64_t ldk, int mp, int np, int batch = 1, int64_t strideX1 = 0,
+                  int64_t strideX2 = 0, int64_t strideK = 0, const ProblemParams* pp_dev = nullptr);
 int gpk_cov_deriv(gpk_handle h, int param_num, const double* dX, int n, int64_t ldx, const CovParams& cp,
                   double sf, double sn, const double* ls_host, double* dK, int64_t ldk);
 
@@ -113,38 +132,43 @@ int gpk_cov_deriv(gpk_handle h, int param_num, const double* dX, int n, int64_t 
 // factorisation (gpk_chol.cu): A (N x N, ld N, lower, padded) -> L in place (lower part; when
 // keep_L is 0 the off-diagonal blocks of A are left in an unspecified state, only diag(L) and the
 // diagonal 128-blocks are valid), Li = L^-1 (N x N, ld N, lower; upper parts of diagonal blocks zeroed;
-// blocks above the diagonal untouched).  T: scratch of at least gpk_chol_scratch_doubles(N).
+// blocks above the diagonal untouched).  T: scratch of at least gpk_chol_scratch_doubles(N) per problem.
+// info_dev[b] receives 0 or the failing leading minor (1-based) of problem b.
 // ---------------------------------------------------------------------------------------------
-// base case (gpk_base.cu): batch of 128x128 blocks; mode 0 = factor + invert, mode 1 = invert a given lower factor
-int gpk_base_potrf_trtri(gpk_handle h, double* A, int64_t lda, double* Li, int64_t ldi, int col_offset, int mode, int batch,
-                         int64_t strideA, int64_t strideLi);
+// base case (gpk_base.cu): `batch` 128x128 blocks at A + i*strideA; mode 0 = factor + invert, mode 1 = invert a given
+// lower factor.  Block i reports into info[i*info_stride] with column offset col_offset + i*coloff_stride.
+int gpk_base_potrf_trtri(gpk_handle h, double* A, int64_t lda, double* Li, int64_t ldi, int* info, int col_offset, int mode,
+                         int batch, int64_t strideA, int64_t strideLi, int info_stride, int coloff_stride);
 size_t gpk_chol_scratch_doubles(int N);
-int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int col_offset);
+int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int* info_dev, int batch = 1);
 // L^-1 for a given lower-triangular L (N x N padded, ld N)
 int gpk_trtri_lower(gpk_handle h, const double* L, double* Li, double* T, int N);
 // Kinv (lower triangle incl. diagonal tiles in full) = Li^t Li
-int gpk_lauum_lower(gpk_handle h, const double* Li, double* Kinv, int N);
+int gpk_lauum_lower(gpk_handle h, const double* Li, double* Kinv, int N, int batch = 1);
 
 // ---------------------------------------------------------------------------------------------
 // vectors / reductions / gradient (gpk_vec.cu, gpk_grad.cu)
 // ---------------------------------------------------------------------------------------------
-// z = Li * y (lower-triangular matvec, N padded; y has N entries with zeros in the padding)
-int gpk_trmv_lower(gpk_handle h, const double* Li, int N, const double* y, double* z, double* scratch);
+// z = Li * y (lower-triangular matvec, N padded; y has N entries with zeros in the padding); scratch: (N/1024+1)*N per problem
+int gpk_trmv_lower(gpk_handle h, const double* Li, int N, const double* y, double* z, double* scratch, int batch = 1);
 // a = Li^t * z
-int gpk_trmv_lower_t(gpk_handle h, const double* Li, int N, const double* z, double* a);
+int gpk_trmv_lower_t(gpk_handle h, const double* Li, int N, const double* z, double* a, int batch = 1);
 // out[c] = sum_r M[r + c*ld] * v[r]  (square != 0: sum_r M[r + c*ld]^2), one warp per column
-int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int cols, const double* v, double* out, int square);
-// out[0] = -0.5*y.alpha - sum_{i<n} log(diag_i(A)) - 0.5*n*log(2 pi)   (GpPredictor.scala:144-149)
-int gpk_loglik(gpk_handle h, const double* A, int N, int n, const double* y, const double* alpha, double* out);
-// g[p] = 0.5 * sum_{i,j<n} (alpha_i alpha_j - Kinv_ij) * dk_p(x_i,x_j,i==j)  for p < nparams
+int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int cols, const double* v, double* out, int square,
+                    int batch = 1, int64_t strideM = 0, int64_t strideV = 0, int64_t strideOut = 0);
+// out[b*strideOut] = -0.5*y.alpha - sum_{i<n} log(diag_i(A)) - 0.5*n*log(2 pi)   (GpPredictor.scala:144-149)
+int gpk_loglik(gpk_handle h, const double* A, int N, int n, const double* y, const double* alpha, double* out, int batch = 1,
+               int64_t strideOut = 0);
+// g[b*strideOut + p] = 0.5 * sum_{i,j<n} (alpha_i alpha_j - Kinv_ij) * dk_p(x_i,x_j,i==j)  for p < nparams
 int gpk_grad_trace(gpk_handle h, const double* Kinv, int N, const double* dX, int n, int64_t ldx, const double* alpha,
-                   const CovParams& cp, double sf, double sn, const double* ls_host, int nparams, double* g_out,
-                   double* scratch);
+                   const ProblemParams& pp, int nparams, double* g_out, double* scratch, int batch = 1, int64_t strideX = 0,
+                   const ProblemParams* pp_dev = nullptr, int64_t strideOut = 0);
 size_t gpk_grad_scratch_doubles(int N, int D);
 
 // misc elementwise helpers (gpk_vec.cu)
 int gpk_copy2d(gpk_handle h, double* dst, int64_t ldd, const double* src, int64_t lds, int rows, int cols);
-int gpk_pad_vector(gpk_handle h, double* dst, int N, const double* src, int n);
+// dst[b*N + i] = i < n ? src[b*n + i] : 0
+int gpk_pad_vector(gpk_handle h, double* dst, int N, const double* src, int n, int batch = 1);
 // dst (N x N padded, lower + identity padding) from src (n x n, ld lds); optionally checks symmetry -> d_flag
 int gpk_load_sym_padded(gpk_handle h, double* dst, int N, const double* src, int n, int64_t lds, int* d_notsym);
 // dst (n x n, ld) = lower triangle of src (N x N) with zeros above the diagonal

@@ -1,20 +1,25 @@
 // gpk_vec.cu -- O(n^2) / O(n) pieces of the path: triangular matrix-vector products (the alpha = L^-t (L^-1 y)
 // solves of GpPredictor.scala:121-122, done with the explicit inverse that gpk_chol.cu produces), the
 // log-marginal-likelihood reduction (GpPredictor.scala:144-149), padding / triangle copies at the ABI.
-// All reductions are order-deterministic (no floating-point atomics).
+// All reductions are order-deterministic (no floating-point atomics).  Every kernel is batched over independent
+// problems through a grid dimension (matrix b at base + b*N*N, vector b at base + b*N).
 #include "gpk_internal.cuh"
 
 namespace {
 
 constexpr int KCH = 1024;  // k-chunk of the split-k lower matvec
 
-// partial[chunk][r] = sum_{k in chunk, k < rowblock_end} Li[r + k*N] * y[k]
+// partial[b][chunk][r] = sum_{k in chunk, k < rowblock_end} Li_b[r + k*N] * y_b[k]
 __global__ void __launch_bounds__(128) trmv_lower_partial(const double* __restrict__ Li, int N, const double* __restrict__ y,
-                                                          double* __restrict__ partial) {
+                                                          double* __restrict__ partial, int nch) {
     const int rb = blockIdx.x, ch = blockIdx.y;
+    const int64_t b = blockIdx.z;
     const int k0 = ch * KCH;
     const int rend = (rb + 1) * GPK_TILE;
     if (k0 >= rend) return;
+    Li += b * (int64_t)N * N;
+    y += b * N;
+    partial += b * (int64_t)nch * N;
     const int k1 = min(k0 + KCH, rend);
     const int r = rb * GPK_TILE + threadIdx.x;
     const double* col = Li + r + (int64_t)k0 * N;
@@ -31,21 +36,27 @@ __global__ void __launch_bounds__(128) trmv_lower_partial(const double* __restri
     partial[(int64_t)ch * N + r] = (a0 + a1) + (a2 + a3);
 }
 
-__global__ void trmv_lower_finish(const double* __restrict__ partial, int N, double* __restrict__ z) {
+__global__ void trmv_lower_finish(const double* __restrict__ partial, int N, double* __restrict__ z, int nch) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
     if (r >= N) return;
+    partial += b * (int64_t)nch * N;
     const int rend = (r / GPK_TILE + 1) * GPK_TILE;
     double acc = 0.0;
     for (int ch = 0; ch * KCH < rend; ++ch) acc += partial[(int64_t)ch * N + r];
-    z[r] = acc;
+    z[b * N + r] = acc;
 }
 
 // out[c] = sum_{r >= rstart(c)} M[r + c*ld] * v[r]; one warp per column.  tri != 0: rstart = 128-block of c.
 __global__ void __launch_bounds__(256) colwise_dot(const double* __restrict__ M, int64_t ld, int rows, int cols,
-                                                   const double* __restrict__ v, double* __restrict__ out, int tri,
-                                                   int square) {
+                                                   const double* __restrict__ v, double* __restrict__ out, int tri, int square,
+                                                   int64_t strideM, int64_t strideV, int64_t strideOut) {
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (c >= cols) return;
+    const int64_t b = blockIdx.y;
+    M += b * strideM;
+    if (v) v += b * strideV;
+    out += b * strideOut;
     const int lane = threadIdx.x & 31;
     const int rs = tri ? (c / GPK_TILE) * GPK_TILE : 0;
     const double* col = M + (int64_t)c * ld;
@@ -64,8 +75,13 @@ __global__ void __launch_bounds__(256) colwise_dot(const double* __restrict__ M,
 }
 
 __global__ void __launch_bounds__(256) loglik_kernel(const double* __restrict__ A, int N, int n, const double* __restrict__ y,
-                                                     const double* __restrict__ alpha, double* __restrict__ out) {
+                                                     const double* __restrict__ alpha, double* __restrict__ out,
+                                                     int64_t strideOut) {
     __shared__ double sd[256], sl[256];
+    const int64_t b = blockIdx.x;
+    A += b * (int64_t)N * N;
+    y += b * N;
+    alpha += b * N;
     double d = 0.0, l = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) {
         d += y[i] * alpha[i];
@@ -77,12 +93,13 @@ __global__ void __launch_bounds__(256) loglik_kernel(const double* __restrict__ 
         if (threadIdx.x < s) { sd[threadIdx.x] += sd[threadIdx.x + s]; sl[threadIdx.x] += sl[threadIdx.x + s]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = -0.5 * sd[0] - sl[0] - 0.5 * n * log(2.0 * 3.14159265358979323846);
+    if (threadIdx.x == 0) out[b * strideOut] = -0.5 * sd[0] - sl[0] - 0.5 * n * log(2.0 * 3.14159265358979323846);
 }
 
 __global__ void pad_vector_kernel(double* dst, int N, const double* src, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) dst[i] = (i < n) ? src[i] : 0.0;
+    const int64_t b = blockIdx.y;
+    if (i < N) dst[b * N + i] = (i < n) ? src[b * n + i] : 0.0;
 }
 
 // dst (N x N): lower triangle (and full diagonal 128-blocks) of the symmetric src, identity padding.
@@ -124,30 +141,33 @@ __global__ void store_tri_kernel(double* dst, int64_t ldd, const double* src, in
 
 }  // namespace
 
-int gpk_trmv_lower(gpk_handle h, const double* Li, int N, const double* y, double* z, double* scratch) {
-    dim3 grid(N / GPK_TILE, (N + KCH - 1) / KCH);
-    trmv_lower_partial<<<grid, 128, 0, h->stream>>>(Li, N, y, scratch);
+int gpk_trmv_lower(gpk_handle h, const double* Li, int N, const double* y, double* z, double* scratch, int batch) {
+    const int nch = (N + KCH - 1) / KCH;
+    dim3 grid(N / GPK_TILE, nch, batch);
+    trmv_lower_partial<<<grid, 128, 0, h->stream>>>(Li, N, y, scratch, nch);
     GPK_LAUNCH_CHECK(h);
-    trmv_lower_finish<<<(N + 255) / 256, 256, 0, h->stream>>>(scratch, N, z);
-    GPK_LAUNCH_CHECK(h);
-    return GPK_OK;
-}
-
-int gpk_trmv_lower_t(gpk_handle h, const double* Li, int N, const double* z, double* a) {
-    colwise_dot<<<(N + 7) / 8, 256, 0, h->stream>>>(Li, N, N, N, z, a, 1, 0);
+    trmv_lower_finish<<<dim3((N + 255) / 256, batch), 256, 0, h->stream>>>(scratch, N, z, nch);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }
 
-int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int cols, const double* v, double* out, int square) {
+int gpk_trmv_lower_t(gpk_handle h, const double* Li, int N, const double* z, double* a, int batch) {
+    colwise_dot<<<dim3((N + 7) / 8, batch), 256, 0, h->stream>>>(Li, N, N, N, z, a, 1, 0, (int64_t)N * N, N, N);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int cols, const double* v, double* out, int square,
+                    int batch, int64_t strideM, int64_t strideV, int64_t strideOut) {
     if (cols <= 0) return GPK_OK;
-    colwise_dot<<<(cols + 7) / 8, 256, 0, h->stream>>>(M, ld, rows, cols, v, out, 0, square);
+    colwise_dot<<<dim3((cols + 7) / 8, batch), 256, 0, h->stream>>>(M, ld, rows, cols, v, out, 0, square, strideM, strideV, strideOut);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }
 
-int gpk_loglik(gpk_handle h, const double* A, int N, int n, const double* y, const double* alpha, double* out) {
-    loglik_kernel<<<1, 256, 0, h->stream>>>(A, N, n, y, alpha, out);
+int gpk_loglik(gpk_handle h, const double* A, int N, int n, const double* y, const double* alpha, double* out, int batch,
+               int64_t strideOut) {
+    loglik_kernel<<<batch, 256, 0, h->stream>>>(A, N, n, y, alpha, out, strideOut);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }
@@ -156,12 +176,11 @@ int gpk_copy2d(gpk_handle h, double* dst, int64_t ldd, const double* src, int64_
     if (rows <= 0 || cols <= 0) return GPK_OK;
     GPK_CUDA(h, cudaMemcpy2DAsync(dst, ldd * sizeof(double), src, lds * sizeof(double), (size_t)rows * sizeof(double),
                                   (size_t)cols, cudaMemcpyDeviceToDevice, h->stream));
-    h->launches++;
     return GPK_OK;
 }
 
-int gpk_pad_vector(gpk_handle h, double* dst, int N, const double* src, int n) {
-    pad_vector_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(dst, N, src, n);
+int gpk_pad_vector(gpk_handle h, double* dst, int N, const double* src, int n, int batch) {
+    pad_vector_kernel<<<dim3((N + 255) / 256, batch), 256, 0, h->stream>>>(dst, N, src, n);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }

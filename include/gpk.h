@@ -129,6 +129,29 @@ int gpk_gp_predict(gpk_handle h, const double* X, int n, int D, int64_t ldx, con
                    const double* Xs, int ms, int64_t ldxs, const double* theta, int has_sigma_noise,
                    double sigma_noise, double* mean, double* sigma, int64_t lds, double* ll);
 
+/* ---- batched independent GPs (BASELINE.json config 4) ---------------------------------------------
+ * B problems of one shape (n, D) per call: MLE restarts (GpPredictor.scala:126-142 evaluated from several
+ * start points), one GP per state / observation dimension (GPUnscentedKalmanFilter.scala:123-136), GP-UCB
+ * restarts (GPOptimizer.scala:54-61).  Problem b uses X + b*strideX (strideX == 0: every problem shares X, the
+ * GP-UKF case), y + b*n and thetas + b*(D+2).  Results: ll[b], grad[b*nparams + p], info[b] (0, or the failing
+ * leading minor of problem b; may be NULL).  Returns GPK_ENOTPD if any problem failed; the others are valid.
+ * Problems never interact, so any partition of the batch over handles / GPUs gives identical results. */
+int gpk_gp_nll_grad_batched(gpk_handle h, int B, const double* X, int n, int D, int64_t ldx, int64_t strideX,
+                            const double* y, const double* thetas, int has_sigma_noise, double sigma_noise,
+                            int nparams, double* ll, double* grad, int* info);
+/* Device-resident variant: out_dev[b*(nparams+1)] = ll_b followed by nparams gradients; info_dev[b]; thetas on
+ * the HOST.  Asynchronous on the handle's stream. */
+int gpk_gp_nll_grad_batched_dev(gpk_handle h, int B, const double* dX, int n, int D, int64_t ldx, int64_t strideX,
+                                const double* dy, const double* thetas_host, int has_sigma_noise, double sigma_noise,
+                                int nparams, double* out_dev, int* info_dev);
+/* Fit B GPs and evaluate each at its own ms test rows (Xs + b*strideXs; strideXs == 0: shared test rows):
+ * mean[b*ms + i], var[b*ms + i] = diag of computePosterior's sigma (includes noiseVar^2), ll[b] (may be NULL).
+ * This is the GP-UKF sigma-point pattern (GPUnscentedKalmanFilter.scala:77-88,138-147) with m = 2d+1 rows. */
+int gpk_gp_predict_batched(gpk_handle h, int B, const double* X, int n, int D, int64_t ldx, int64_t strideX,
+                           const double* y, const double* thetas, const double* Xs, int ms, int64_t ldxs,
+                           int64_t strideXs, int has_sigma_noise, double sigma_noise, double* mean, double* var,
+                           double* ll, int* info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,94 @@
+"""GPU parity for the batched independent-GP entry points (BASELINE.json config 4) through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+import gp_algos_b200 as gp
+from gp_algos_b200 import batched
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-9
+
+
+def _grad_ok(g, go):
+    floor = RTOL * np.abs(go).max()
+    return np.all(np.abs(g - go) <= RTOL * np.maximum(np.abs(go), floor))
+
+
+def test_golden_c4_small_batched():
+    g = np.load(os.path.join(G, "c4_small.npz"))
+    B = int(g["B"])
+    X = np.stack([g[f"X{b}"] for b in range(B)]); ys = np.stack([g[f"y{b}"] for b in range(B)])
+    th = np.stack([g[f"theta{b}"] for b in range(B)]); Xs = np.stack([g[f"Xs{b}"] for b in range(B)])
+    ll, grad, info = batched.log_likelihood_with_derivatives_batched(X, ys, th)
+    assert np.all(info == 0)
+    for b in range(B):
+        assert abs(ll[b] - float(g[f"ll{b}"])) <= RTOL * abs(float(g[f"ll{b}"]))
+        assert _grad_ok(grad[b], g[f"grad{b}"])
+    mean, var, ll2, info = batched.predict_batched(X, ys, th, Xs)
+    assert np.all(info == 0)
+    for b in range(B):
+        assert np.all(np.abs(mean[b] - g[f"mean{b}"]) <= RTOL * np.abs(g[f"mean{b}"]).max())
+        assert np.all(np.abs(var[b] - g[f"var{b}"]) <= RTOL * np.abs(g[f"var{b}"]))
+        assert abs(ll2[b] - float(g[f"ll{b}"])) <= RTOL * abs(float(g[f"ll{b}"]))
+
+
+def test_batched_equals_single_calls_and_shared_x():
+    """GP-UKF flavour: one X shared by every output dimension (GPUnscentedKalmanFilter.scala:123-136)."""
+    B, n, D, m = 5, 300, 4, 9
+    rng = np.random.default_rng(4)
+    X = rng.uniform(0, 1, size=(n, D)); Xs = rng.uniform(0, 1, size=(m, D))
+    ys = np.stack([np.sin(X @ rng.standard_normal(D)) + 0.1 * rng.standard_normal(n) for _ in range(B)])
+    th = np.stack([orc.pack_theta(10 ** rng.uniform(-0.3, 0.3), 10 ** rng.uniform(-0.5, 0.2, size=D), 0.1) for _ in range(B)])
+    ll, grad, info = batched.log_likelihood_with_derivatives_batched(X, ys, th)
+    mean, var, ll2, _ = batched.predict_batched(X, ys, th, Xs)
+    for b in range(B):
+        p = gp.GpPredictor(gp.GaussianRbfKernel(gp.GaussianRbfParams(th[b, 0], th[b, 1:-1], th[b, -1])))
+        l1, g1 = p.logLikelihoodWithDerivatives(gp.PredictionTrainingInput(X, None, ys[b]), th[b], D + 2)
+        assert l1 == ll[b] and np.array_equal(g1, grad[b])           # same kernels, same order: bit-identical
+        llo, go = orc.lit_loglik_with_derivs(X, ys[b], th[b])
+        assert abs(ll[b] - llo) <= RTOL * abs(llo) and _grad_ok(grad[b], go)
+        Lo, ao = orc.lit_precompute(X, ys[b], th[b])
+        mo, So, _ = orc.lit_compute_posterior(X, Xs, Lo, ao, th[b])
+        assert np.all(np.abs(mean[b] - mo) <= RTOL * np.abs(mo).max())
+        assert np.all(np.abs(var[b] - np.diag(So)) <= RTOL * np.abs(np.diag(So)))
+    # partitioning the batch (what each GPU rank does) does not change any result
+    lo, hi = batched.shard_bounds(B, 1, 2)
+    ll_s, grad_s, _ = batched.log_likelihood_with_derivatives_batched(X, ys[lo:hi], th[lo:hi])
+    assert np.array_equal(ll_s, ll[lo:hi]) and np.array_equal(grad_s, grad[lo:hi])
+
+
+def test_batched_failure_is_isolated_per_problem():
+    B, n, D = 4, 200, 2
+    rng = np.random.default_rng(9)
+    X = np.stack([rng.uniform(0, 1, size=(n, D)) for _ in range(B)])
+    X[2, 50] = X[2, 10]                                   # duplicate point in problem 2 ...
+    ys = rng.standard_normal((B, n))
+    th = np.tile(orc.pack_theta(1.0, [0.5, 0.5], 0.1), (B, 1))
+    th[2, -1] = 0.0                                        # ... with zero noise: K_2 is singular
+    ll, grad, info = batched.log_likelihood_with_derivatives_batched(X, ys, th)
+    assert info[2] != 0 and np.all(info[[0, 1, 3]] == 0)
+    for b in (0, 1, 3):
+        llo, go = orc.lit_loglik_with_derivs(X[b], ys[b], th[b])
+        assert abs(ll[b] - llo) <= RTOL * abs(llo) and _grad_ok(grad[b], go)
+
+
+def test_c4_shape_subset_full_n():
+    """Problems of the real C4 shape (n = 1024, D = 8, m = 17), a 24-problem subset against the LAPACK-backed oracle."""
+    B = 24
+    probs = [orc.make_c4_problem(b) for b in range(B)]
+    X = np.stack([p[0] for p in probs]); ys = np.stack([p[1] for p in probs])
+    Xs = np.stack([p[2] for p in probs]); th = np.stack([p[3] for p in probs])
+    ll, grad, info = batched.log_likelihood_with_derivatives_batched(X, ys, th)
+    mean, var, _, _ = batched.predict_batched(X, ys, th, Xs)
+    assert np.all(info == 0)
+    for b in range(0, B, 5):
+        llo, go = orc.fast_loglik_with_derivs(X[b], ys[b], th[b])
+        assert abs(ll[b] - llo) <= RTOL * abs(llo) and _grad_ok(grad[b], go)
+        Lo, ao = orc.fast_precompute(X[b], ys[b], th[b])
+        mo, vo, _ = orc.fast_compute_posterior(X[b], Xs[b], Lo, ao, th[b], full_cov=False)
+        assert np.all(np.abs(mean[b] - mo) <= RTOL * np.abs(mo).max())
+        assert np.all(np.abs(var[b] - vo) <= RTOL * np.abs(vo))
