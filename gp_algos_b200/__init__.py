@@ -7,6 +7,8 @@ and error behaviour), used by the parity tests and the benchmark:
     utils.KernelRequisites  ->  gp_algos_b200.kernel_requisites  (GaussianRbfParams, GaussianRbfKernel)
     utils.MatrixUtils       ->  gp_algos_b200.matrix_utils       (buildKernelMatrix, forwardSolve, ...)
     gp.regression.GpPredictor -> gp_algos_b200.gp_predictor      (GpPredictor, PredictionInput, ...)
+    gp.classification.*      ->  gp_algos_b200.ep_classification (EpParameterEstimator, GpClassifier, ...)
+    (batched independent GPs and their rank sharding: gp_algos_b200.batched)
 
 There is no CPU fallback: importing works anywhere, but every numeric call raises if libgpk.so or a
 CUDA device is missing.
@@ -14,6 +16,9 @@ CUDA device is missing.
 from .kernel_requisites import GaussianRbfKernel, GaussianRbfParams  # noqa: F401
 from .gp_predictor import GpPredictor, PredictionInput, PredictionTrainingInput, GaussianDistribution  # noqa: F401
 from . import matrix_utils as MatrixUtils  # noqa: F401
+from . import batched  # noqa: F401
+from .ep_classification import (EpParameterEstimator, GpClassifier, MarginalLikelihoodEvaluator, SiteParams,  # noqa: F401
+                                AvgBasedStopCriterion, FixedSweeps, ClassifierInput, AfterEstimationClassifierInput)
 from ._lib import GpkError, NotPositiveDefiniteError, MatrixNotSymmetricError, lib_path  # noqa: F401
 
 __all__ = ["GaussianRbfKernel", "GaussianRbfParams", "GpPredictor", "PredictionInput", "PredictionTrainingInput",

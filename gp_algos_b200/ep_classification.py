@@ -1,0 +1,134 @@
+"""Host mirror of gp/classification/{EpParameterEstimator, GpClassifier, MarginalLikelihoodEvaluator}.scala over
+libgpk's EP entry points (gpk_ep_fit, gpk_ep_classify)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from . import matrix_utils as MU
+
+
+@dataclass
+class SiteParams:
+    """EpParameterEstimator.scala:181-182."""
+    tauSiteParams: np.ndarray
+    niSiteParams: np.ndarray
+    marginalLogLikelihood: Optional[float] = None
+
+
+@dataclass
+class AvgBasedStopCriterion:
+    """EpParameterEstimator.scala:187-193: stop when abs(avgBetweenSiteParams(old, current)) < eps (spring-context.xml: 0.01)."""
+    eps: float = 0.01
+    max_sweeps: int = 100
+
+
+@dataclass
+class FixedSweeps:
+    """Run exactly `sweeps` EP sweeps (the R prototype's `for (j in 1:5)`, EpParameterEstimator.scala:147)."""
+    sweeps: int = 5
+
+
+def _stop_args(stop):
+    if isinstance(stop, FixedSweeps):
+        return 0.0, int(stop.sweeps), int(stop.sweeps)
+    if isinstance(stop, AvgBasedStopCriterion):
+        return float(stop.eps), 0, int(stop.max_sweeps)
+    raise TypeError("only AvgBasedStopCriterion / FixedSweeps can be lowered to the GPU path (arbitrary Scala closures cannot)")
+
+
+class EpParameterEstimator:
+    """EpParameterEstimator.scala:11-12: (kernelMatrix, targets, stopCriterion)."""
+
+    def __init__(self, kernelMatrix, targets, stopCriterion, handle=None, keep_linebreak_quirk: bool = True):
+        self.K = _lib.fmat(kernelMatrix)
+        self.targets = np.ascontiguousarray(targets, dtype=np.int32)
+        if self.K.shape[0] != len(self.targets):  # require(...) EpParameterEstimator.scala:20
+            raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, "requirement failed")
+        self.stop = stopCriterion
+        self._handle = handle
+        self.keep_quirk = keep_linebreak_quirk
+        self.sweeps = None
+        self.mu = None
+        self.cavity = None
+
+    @property
+    def estimateSiteParams(self):
+        """-> (SiteParams(tau, nu, Some(logZ)), L)   (EpParameterEstimator.scala:29-69)."""
+        h = self._handle or _lib.default_handle()
+        n = self.K.shape[0]
+        eps, fixed, mx = _stop_args(self.stop)
+        tau = np.empty(n); nu = np.empty(n); mu = np.empty(n); ct = np.empty(n); cn = np.empty(n)
+        L = np.empty((n, n), order="F")
+        logz = C.c_double(); sw = C.c_int()
+        h.check(h.lib.gpk_ep_fit(h.h, _lib.ptr(self.K), n, n, self.targets.ctypes.data_as(C.c_void_p), eps, fixed, mx,
+                                 int(self.keep_quirk), _lib.ptr(tau), _lib.ptr(nu), _lib.ptr(mu), _lib.ptr(L), n, _lib.ptr(ct),
+                                 _lib.ptr(cn), C.addressof(logz), C.addressof(sw)))
+        self.sweeps, self.mu, self.cavity = sw.value, mu, (ct, cn)
+        return SiteParams(tau, nu, logz.value), L
+
+
+@dataclass
+class ClassifierInput:
+    """GpClassifier.scala:63-65."""
+    trainKernelMatrix: np.ndarray
+    targets: np.ndarray
+    initHyperParams: object = None
+    trainData: Optional[np.ndarray] = None
+
+
+@dataclass
+class AfterEstimationClassifierInput:
+    """GpClassifier.scala:58-61."""
+    targets: np.ndarray
+    learnParams: Optional[tuple]
+    hyperParams: object
+    trainKernelMatrix: np.ndarray
+    testTrainKernelMatrix: np.ndarray
+    testKernelMatrix: np.ndarray
+
+
+class GpClassifier:
+    """GpClassifier.scala:11."""
+
+    def __init__(self, stopCriterion, handle=None):
+        self.stopCriterion = stopCriterion
+        self._handle = handle
+
+    def trainClassifier(self, classInput: ClassifierInput):
+        return EpParameterEstimator(classInput.trainKernelMatrix, classInput.targets, self.stopCriterion, self._handle).estimateSiteParams
+
+    def classify(self, input: AfterEstimationClassifierInput) -> np.ndarray:
+        """Class-1 probabilities (GpClassifier.scala:24-47)."""
+        h = self._handle or _lib.default_handle()
+        site, L = input.learnParams if input.learnParams is not None else self.trainClassifier(
+            ClassifierInput(input.trainKernelMatrix, input.targets, input.hyperParams, None))
+        K = _lib.fmat(input.trainKernelMatrix); Ks = _lib.fmat(input.testTrainKernelMatrix); L = _lib.fmat(L)
+        kss = np.ascontiguousarray(np.diag(np.asarray(input.testKernelMatrix, dtype=np.float64)))
+        n, m = K.shape[0], Ks.shape[0]
+        tau = np.ascontiguousarray(site.tauSiteParams, dtype=np.float64); nu = np.ascontiguousarray(site.niSiteParams, dtype=np.float64)
+        prob = np.empty(m); self.fMean = np.empty(m); self.fVariance = np.empty(m)
+        h.check(h.lib.gpk_ep_classify(h.h, _lib.ptr(K), n, n, _lib.ptr(Ks), m, m, _lib.ptr(kss), _lib.ptr(tau), _lib.ptr(nu),
+                                      _lib.ptr(L), n, _lib.ptr(prob), _lib.ptr(self.fMean), _lib.ptr(self.fVariance)))
+        return prob
+
+
+class MarginalLikelihoodEvaluator:
+    """MarginalLikelihoodEvaluator.scala:13 -- the K-build + EP + logZ entry points (:18-31).  The hyper-parameter
+    gradient (:33-66) is a SURVEY.md 8(f) "next" row and is not lowered yet."""
+
+    def __init__(self, stopCriterion, kernelFunc, handle=None):
+        self.stopCriterion, self.kernelFunc, self._handle = stopCriterion, kernelFunc, handle
+
+    def logLikelihoodWithKernelMatrixPassed(self, kernelMatrix, targets) -> float:
+        site, _ = EpParameterEstimator(kernelMatrix, targets, self.stopCriterion, self._handle).estimateSiteParams
+        return site.marginalLogLikelihood
+
+    def logLikelihoodWithoutGrad(self, trainInput, targets, hyperParams) -> float:
+        kf = self.kernelFunc.changeHyperParams(hyperParams)
+        K = MU.buildKernelMatrix(kf, trainInput, handle=self._handle)
+        return self.logLikelihoodWithKernelMatrixPassed(K, targets)

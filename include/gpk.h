@@ -152,6 +152,25 @@ int gpk_gp_predict_batched(gpk_handle h, int B, const double* X, int n, int D, i
                            int64_t strideXs, int has_sigma_noise, double sigma_noise, double* mean, double* var,
                            double* ll, int* info);
 
+/* ---- EP binary GP classification (BASELINE.json config 3) ------------------------------------------
+ * gp/classification/EpParameterEstimator.scala:29-69 estimateSiteParams (+ :71-96 epMarginalLikelihood, :98-109
+ * marginalMoments, :187-202 AvgBasedStopCriterion).  K: n x n symmetric kernel matrix (the reference is handed a
+ * prebuilt K too), targets in {-1,+1} (DenseVector[Int]).  Stop rule: fixed_sweeps > 0 runs exactly that many sweeps,
+ * otherwise sweeps continue until abs(avgBetweenSiteParams) < eps (at least one sweep, at most max_sweeps).
+ * keep_linebreak_quirk != 0 reproduces the reference AS COMPILED: the statement at EpParameterEstimator.scala:91 ends
+ * at the newline, so the "fourth and first" term of log Z is dropped; 0 includes it (R&W eq. 3.65).
+ * Outputs (any may be NULL): tau, nu, mu[n], L (n x n lower factor of I + S^1/2 K S^1/2), cav_tau, cav_nu[n], logZ,
+ * sweeps.  The site loop runs as blocked delayed updates on the device (see csrc/gpk_ep.cu). */
+int gpk_ep_fit(gpk_handle h, const double* K, int n, int64_t ldk, const int* targets, double eps, int fixed_sweeps,
+               int max_sweeps, int keep_linebreak_quirk, double* tau, double* nu, double* mu, double* L, int64_t ldl,
+               double* cav_tau, double* cav_nu, double* logZ, int* sweeps);
+/* gp/classification/GpClassifier.scala:24-47 classify with learnParams = (siteParams, L): K n x n, Ks m x n
+ * (test-train), kss_diag[m] = diagonal of the test kernel matrix (only the diagonal is read, :44).
+ * prob[m] = Phi(fmean / sqrt(1 + fvar)); fmean / fvar optional. */
+int gpk_ep_classify(gpk_handle h, const double* K, int n, int64_t ldk, const double* Ks, int m, int64_t ldks,
+                    const double* kss_diag, const double* tau, const double* nu, const double* L, int64_t ldl,
+                    double* prob, double* fmean, double* fvar);
+
 #ifdef __cplusplus
 }
 #endif

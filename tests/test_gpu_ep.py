@@ -1,0 +1,81 @@
+"""GPU parity for EP binary classification (BASELINE.json config 3) through the C ABI: tau, nu, logZ, class
+probabilities at 1e-9 with identical sweep counts.  The reference has NO test for this path
+("parity unpinned"): the oracle is its line-by-line C restatement, cross-checked against a NumPy flavour in tests/."""
+import os
+
+import numpy as np
+import pytest
+
+import gp_algos_b200 as gp
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-9
+
+
+def close(a, b, rtol=RTOL):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), np.abs(b).max() * 1e-6))
+
+
+def test_golden_c3_small():
+    g = np.load(os.path.join(G, "c3_small.npz"))
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(g["theta"][0], g["theta"][1:-1], g["theta"][-1]))
+    K = gp.MatrixUtils.buildKernelMatrix(kf, g["X"])
+    site, L = gp.EpParameterEstimator(K, g["targets"], gp.FixedSweeps(5)).estimateSiteParams
+    assert close(site.tauSiteParams, g["tau5"]) and close(site.niSiteParams, g["nu5"])
+    assert abs(site.marginalLogLikelihood - float(g["logZ5"])) <= RTOL * abs(float(g["logZ5"]))
+    assert close(np.diag(L), g["L5_diag"])
+    est = gp.EpParameterEstimator(K, g["targets"], gp.AvgBasedStopCriterion(0.01))   # shipped criterion
+    site, L = est.estimateSiteParams
+    assert est.sweeps == int(g["sweeps"])
+    assert close(site.tauSiteParams, g["tau"]) and close(site.niSiteParams, g["nu"])
+    assert abs(site.marginalLogLikelihood - float(g["logZ"])) <= RTOL * abs(float(g["logZ"]))
+    Ks = gp.MatrixUtils.buildKernelMatrix(kf, g["Xs"], g["X"]); Kss = gp.MatrixUtils.buildKernelMatrix(kf, g["Xs"])
+    clf = gp.GpClassifier(gp.AvgBasedStopCriterion(0.01))
+    p = clf.classify(gp.AfterEstimationClassifierInput(g["targets"], (site, L), None, K, Ks, Kss))
+    assert close(p, g["prob"]) and close(clf.fMean, g["fmean"]) and close(clf.fVariance, g["fvar"])
+
+
+@pytest.mark.parametrize("n,D,sweeps", [(50, 2, 2), (130, 3, 3), (300, 4, 2)])
+def test_ep_vs_literal_oracle(n, D, sweeps):
+    X, t, th = orc.make_c3(n=n, D=D, seed=n)
+    K = orc.lit_build_kernel_matrix(X, th)
+    site, L = gp.EpParameterEstimator(K, t, gp.FixedSweeps(sweeps)).estimateSiteParams
+    o = orc.lit_ep_estimate(K, t, fixed_sweeps=sweeps)
+    assert close(site.tauSiteParams, o["tau"]) and close(site.niSiteParams, o["nu"])
+    assert abs(site.marginalLogLikelihood - o["logZ"]) <= RTOL * abs(o["logZ"])
+    assert np.allclose(L, o["L"], rtol=1e-9, atol=1e-12)
+    # without the line-break quirk the dropped term reappears (EpParameterEstimator.scala:91-92)
+    site2, _ = gp.EpParameterEstimator(K, t, gp.FixedSweeps(sweeps), keep_linebreak_quirk=False).estimateSiteParams
+    o2 = orc.lit_ep_estimate(K, t, fixed_sweeps=sweeps, keep_quirk=False)
+    assert abs(site2.marginalLogLikelihood - o2["logZ"]) <= RTOL * abs(o2["logZ"])
+
+
+def test_ep_classifier_end_to_end_vs_fast_oracle():
+    X, t, th = orc.make_c3(n=700, D=4, seed=3)
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
+    Xs = np.random.default_rng(1).standard_normal((40, 4))
+    K = gp.MatrixUtils.buildKernelMatrix(kf, X); Ks = gp.MatrixUtils.buildKernelMatrix(kf, Xs, X); Kss = gp.MatrixUtils.buildKernelMatrix(kf, Xs)
+    clf = gp.GpClassifier(gp.AvgBasedStopCriterion(0.01))
+    site, L = clf.trainClassifier(gp.ClassifierInput(K, t))
+    o = orc.fast_ep_estimate(K, t, eps=0.01)
+    assert close(site.tauSiteParams, o["tau"]) and close(site.niSiteParams, o["nu"])
+    assert abs(site.marginalLogLikelihood - o["logZ"]) <= RTOL * abs(o["logZ"])
+    p = clf.classify(gp.AfterEstimationClassifierInput(t, (site, L), None, K, Ks, Kss))
+    po, fmo, fvo = orc.fast_ep_classify(K, Ks, Kss, o["tau"], o["nu"], o["L"])
+    assert close(p, po)
+    # MarginalLikelihoodEvaluator.logLikelihoodWithoutGrad (MarginalLikelihoodEvaluator.scala:24-31)
+    ev = gp.MarginalLikelihoodEvaluator(gp.AvgBasedStopCriterion(0.01), kf)
+    assert abs(ev.logLikelihoodWithoutGrad(X, t, th) - o["logZ"]) <= RTOL * abs(o["logZ"])
+    # training accuracy sanity: probabilities on the training inputs side with the labels
+    ptrain = clf.classify(gp.AfterEstimationClassifierInput(t, (site, L), None, K, K, K))
+    assert np.mean((ptrain > 0.5) == (t > 0)) > 0.85
+
+
+def test_ep_requirements():
+    with pytest.raises(ValueError):  # require(kernelMatrix.rows == targets.length)
+        gp.EpParameterEstimator(np.eye(4), np.ones(3, dtype=np.int32), gp.FixedSweeps(1))
+    with pytest.raises(TypeError):
+        gp.EpParameterEstimator(np.eye(4), np.ones(4, dtype=np.int32), lambda ctx: True).estimateSiteParams
