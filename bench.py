@@ -254,7 +254,7 @@ def run_gpk(args):
             best = min(best, s0.elapsed_time(s1))
         peak = 2.0 * n ** 3 / best * 1e-9
         ach = syrk_flops / syrk_ms * 1e-9
-        roofline = {"kernel": "gemm_f64_dmma_kernel<false,false> as the Cholesky trailing update (SYRK lower, "
+        roofline = {"kernel": "gemm_f64_dmma_kernel<false,false,SmallTile 64x64> as the Cholesky trailing update (SYRK lower, "
                               f"n={nn}, k={kk})", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": ach / peak, "traffic": None,
                     "peak_source": f"cuBLAS Dgemm {n}^3 measured live in this run (MEASURED_PEAKS.json has no FP64 entry; "

@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int TK = 16, STAGES = 4;
+constexpr int TK = 16;
 constexpr int LDK = TK + 4;  // row stride (doubles) of a [x][k] stage   (k-contiguous source)
 constexpr int GROUP_S = 8;   // raster: blocks walk bands of 8 s-tiles so a wave shares operand panels in L2
 
@@ -41,18 +41,20 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 //   Big  : 2 x 4 warps, 8 x 4 blocks -> 128 x 128 CTA tile, 256 threads, 1 CTA/SM   (throughput)
 //   Small: 2 x 2 warps, 4 x 4 blocks ->  64 x  64 CTA tile, 128 threads, 2 CTAs/SM  (few-tile problems: spreads a
 //          128-tile over 4 SMs; one SM can only retire 0.25 TFLOP/s of FP64)
-template <int WR_, int WS_, int BI_, int BJ_>
+template <int WR_, int WS_, int BI_, int BJ_, int STAGES_, int MINB_>
 struct TileCfg {
-    static constexpr int WR = WR_, WS = WS_, BI = BI_, BJ = BJ_;
+    static constexpr int WR = WR_, WS = WS_, BI = BI_, BJ = BJ_, STAGES = STAGES_;
     static constexpr int TR = WR * BI * 8, TS = WS * BJ * 8, NT = 32 * WR * WS;
     static constexpr int LDRP = TR + 4, LDRQ = TS + 4;  // row stride of a [k][x] stage (x-contiguous source), %16 == 4
     static constexpr int P_STAGE = (TR * LDK > TK * LDRP) ? TR * LDK : TK * LDRP;
     static constexpr int Q_STAGE = (TS * LDK > TK * LDRQ) ? TS * LDK : TK * LDRQ;
     static constexpr size_t SMEM = (size_t)STAGES * (P_STAGE + Q_STAGE) * sizeof(double);
-    static constexpr int MIN_BLOCKS = (NT >= 256) ? 1 : 2;
+    static constexpr int MIN_BLOCKS = MINB_;
 };
-using BigTile = TileCfg<2, 4, 8, 4>;
-using SmallTile = TileCfg<2, 2, 4, 4>;
+using BigTile = TileCfg<2, 4, 8, 4, 4, 1>;
+using WideTile = TileCfg<4, 4, 4, 4, 4, 1>;    // 128 x 128 tile on 16 warps of 32 x 32 (4 warps per scheduler)
+using MidTile = TileCfg<2, 2, 8, 4, 3, 2>;     // 128 x 64 tile, 4 warps of 64 x 32, 2 CTAs per SM
+using SmallTile = TileCfg<2, 2, 4, 4, 3, 3>;   // 3 stages x 20 KB = 60 KB -> 3 CTAs (12 warps) per SM
 
 // stage a TX (x) by 16 (k) operand tile
 template <bool KC, int TX, int NT>
@@ -79,7 +81,7 @@ __device__ __forceinline__ void load_tile(double* st, const double* g, int64_t l
 template <bool PK, bool QK, class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_BLOCKS) gemm_f64_dmma_kernel(const GemmDesc g) {
     constexpr int TR = Cfg::TR, TS = Cfg::TS, NT = Cfg::NT, BI = Cfg::BI, BJ = Cfg::BJ;
-    constexpr int LDRP = Cfg::LDRP, LDRQ = Cfg::LDRQ;
+    constexpr int LDRP = Cfg::LDRP, LDRQ = Cfg::LDRQ, STAGES = Cfg::STAGES;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int tilesS = g.S / TS, tilesR = g.R / TR;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_BLOCKS) gemm_f64_dmma_kernel
 
 template <bool PK, bool QK, class Cfg>
 int launch(gpk_handle h, const GemmDesc& g, int cfg_id) {
-    const unsigned bit = 1u << (16 + cfg_id * 4 + (PK ? 2 : 0) + (QK ? 1 : 0));
+    const unsigned bit = 1u << (12 + cfg_id * 4 + (PK ? 2 : 0) + (QK ? 1 : 0));
     if (!(h->func_cfg & bit)) {
         GPK_CUDA(h, cudaFuncSetAttribute(gemm_f64_dmma_kernel<PK, QK, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::SMEM));
@@ -200,7 +202,10 @@ int small_tile_threshold() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("GPK_SMALL_TILE_THRESHOLD");
-        v = e ? atoi(e) : 296;  // fewer 128-tiles than ~2 waves of 148 SMs -> 64x64 tiles
+        // Measured on B200 (profiles/r01_tile_configs.txt): 64x64 tiles at 3 CTAs/SM beat the 128x128 (1 CTA/SM) and
+        // 128x64 (2 CTAs/SM) configurations at every size (SYRK n=k=4096: 31.2 vs 26.8 vs 29.1 TFLOP/s), so they are
+        // the default everywhere; the threshold stays as a tuning knob.
+        v = e ? atoi(e) : 0x7fffffff;
     }
     return v;
 }
@@ -215,5 +220,9 @@ int gpk_gemm(gpk_handle h, const GemmDesc& g) {
     int64_t tiles = (int64_t)(g.R / 128) * (g.S / 128) * g.batch;
     if (g.tri_out) tiles = (tiles + g.batch * (g.R / 128)) / 2;
     if (tiles < small_tile_threshold()) return dispatch<SmallTile>(h, g, 1);
+    static int big_kind = -1;
+    if (big_kind < 0) { const char* e = getenv("GPK_BIG_KIND"); big_kind = e ? atoi(e) : 0; }
+    if (big_kind == 1) return dispatch<WideTile>(h, g, 2);
+    if (big_kind == 2) return dispatch<MidTile>(h, g, 3);
     return dispatch<BigTile>(h, g, 0);
 }
