@@ -80,8 +80,12 @@ def load():
         lib.gpk_gp_model_fit.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, cd, C.POINTER(vp), vp]
         lib.gpk_gp_model_from_factor.argtypes = [vp, vp, ci, ci, _i64, vp, _i64, vp, vp, C.POINTER(vp)]
         lib.gpk_gp_model_destroy.argtypes = [vp, vp]
+        lib.gpk_gp_model_get_alpha.argtypes = [vp, vp, vp]
         lib.gpk_gp_model_predict.argtypes = [vp, vp, vp, ci, _i64, ci, vp, vp, _i64, vp, _i64]
         lib.gpk_gp_predict.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, _i64, vp, ci, cd, vp, vp, _i64, vp]
+        lib.gpk_potrf_inv_block_dev.argtypes = [vp, vp, vp, ci, vp]
+        lib.gpk_gemm_nt_dev.argtypes = [vp, ci, ci, ci, cd, vp, _i64, vp, _i64, cd, vp, _i64, ci]
+        lib.gpk_gemv_dev.argtypes = [vp, ci, ci, ci, cd, vp, _i64, vp, cd, vp]
         lib.gpk_ep_fit.argtypes = [vp, vp, ci, _i64, vp, cd, ci, ci, ci, vp, vp, vp, vp, _i64, vp, vp, vp, vp]
         lib.gpk_ep_classify.argtypes = [vp, vp, ci, _i64, vp, ci, _i64, vp, vp, vp, vp, _i64, vp, vp, vp]
         lib.gpk_gp_nll_grad_batched.argtypes = [vp, ci, vp, ci, ci, _i64, _i64, vp, vp, ci, cd, ci, vp, vp, vp]

@@ -314,3 +314,38 @@ int gpk_syrk_lower_dev(gpk_handle h, const double* dP, int64_t ldp, double* dC, 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// device-level building blocks of the multi-GPU block-column Cholesky (BASELINE.json config 5; orchestrated one
+// process per GPU in gp_algos_b200/distributed.py with NCCL panel broadcasts)
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gpk_potrf_inv_block_dev(gpk_handle h, double* dA, double* dLi, int N, int* info_dev) {
+    if (!h || N <= 0 || N % GPK_TILE) return gpk_set_error(h, GPK_EINVAL, "gpk_potrf_inv_block_dev: N must be a multiple of 128");
+    ARENA_OR_FAIL(dT, double*, h, ARENA_T, gpk_chol_scratch_doubles(N) * sizeof(double));
+    return gpk_potrf_inv(h, dA, dLi, dT, N, /*keep_L=*/1, info_dev ? info_dev : h->d_info, 1);
+}
+
+int gpk_gemm_nt_dev(gpk_handle h, int m, int p, int k, double alpha, const double* dP, int64_t ldp, const double* dQ,
+                    int64_t ldq, double beta, double* dC, int64_t ldc, int q_lower_tri) {
+    if (!h || m < 0 || p < 0 || k < 0) return gpk_set_error(h, GPK_EINVAL, "gpk_gemm_nt_dev: bad dimensions");
+    if (m == 0 || p == 0) return GPK_OK;
+    // C(i,c) = alpha sum_k P(i,k) Q(c,k) + beta C(i,c);  D = C^t: r = c, s = i
+    GemmDesc g = gemm_desc();
+    g.P = dQ; g.ldp = ldq; g.p_kcontig = 0;
+    g.Q = dP; g.ldq = ldp; g.q_kcontig = 0;
+    g.D = dC; g.ldd = ldc;
+    if (beta != 0.0) { g.Cin = dC; g.ldc = ldc; }
+    g.R = p; g.S = m; g.K = k; g.alpha = alpha; g.beta = beta;
+    if (q_lower_tri) { g.ke_r = 1; g.heavy_last = 1; }   // Q(c,k) = 0 for k > c
+    return gpk_gemm(h, g);
+}
+
+int gpk_gemv_dev(gpk_handle h, int trans, int m, int ncols, double alpha, const double* dM, int64_t ld, const double* dx,
+                 double beta, double* dy) {
+    if (!h || m < 0 || ncols < 0 || ld < m) return gpk_set_error(h, GPK_EINVAL, "gpk_gemv_dev: bad dimensions");
+    return gpk_gemv(h, trans, m, ncols, alpha, dM, ld, dx, beta, dy);
+}
+
+}  // extern "C"

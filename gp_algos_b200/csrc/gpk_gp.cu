@@ -345,6 +345,13 @@ int gpk_gp_model_from_factor(gpk_handle h, const double* X, int n, int D, int64_
     return GPK_OK;
 }
 
+int gpk_gp_model_get_alpha(gpk_handle h, gpk_model m, double* alpha) {
+    if (!h || !m || !alpha) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_model_get_alpha: bad arguments");
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    GPK_CUDA(h, cudaMemcpyAsync(alpha, m->alpha, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return gpk_synchronize(h);
+}
+
 int gpk_gp_model_predict(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_t ldxs, int want_full_cov, double* mean,
                          double* sigma, int64_t lds, double* V, int64_t ldv) {
     if (!h || !m || ms <= 0 || ldxs < ms || (V && ldv < m->n) || (want_full_cov && sigma && lds < ms))

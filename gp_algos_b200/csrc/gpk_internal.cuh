@@ -156,6 +156,9 @@ int gpk_trmv_lower_t(gpk_handle h, const double* Li, int N, const double* z, dou
 // out[c] = sum_r M[r + c*ld] * v[r]  (square != 0: sum_r M[r + c*ld]^2), one warp per column
 int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int cols, const double* v, double* out, int square,
                     int batch = 1, int64_t strideM = 0, int64_t strideV = 0, int64_t strideOut = 0);
+// y = alpha * op(M) x + beta * y for a column-major m x ncols matrix (trans: y has ncols entries)
+int gpk_gemv(gpk_handle h, int trans, int m, int ncols, double alpha, const double* M, int64_t ld, const double* x, double beta,
+             double* y);
 // out[b*strideOut] = -0.5*y.alpha - sum_{i<n} log(diag_i(A)) - 0.5*n*log(2 pi)   (GpPredictor.scala:144-149)
 int gpk_loglik(gpk_handle h, const double* A, int N, int n, const double* y, const double* alpha, double* out, int batch = 1,
                int64_t strideOut = 0);

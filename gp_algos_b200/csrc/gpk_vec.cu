@@ -96,6 +96,42 @@ __global__ void __launch_bounds__(256) loglik_kernel(const double* __restrict__ 
     if (threadIdx.x == 0) out[b * strideOut] = -0.5 * sd[0] - sl[0] - 0.5 * n * log(2.0 * 3.14159265358979323846);
 }
 
+// y = alpha * M x + beta * y, M m x ncols column-major: one thread per row (coalesced over rows)
+__global__ void __launch_bounds__(128) gemv_n_kernel(int m, int ncols, double alpha, const double* __restrict__ M, int64_t ld,
+                                                     const double* __restrict__ x, double beta, double* __restrict__ y) {
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    if (r >= m) return;
+    const double* p = M + r;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int c = 0;
+    for (; c + 3 < ncols; c += 4) {
+        a0 += p[0] * x[c];
+        a1 += p[ld] * x[c + 1];
+        a2 += p[2 * ld] * x[c + 2];
+        a3 += p[3 * ld] * x[c + 3];
+        p += 4 * ld;
+    }
+    for (; c < ncols; ++c) { a0 += p[0] * x[c]; p += ld; }
+    const double v = alpha * ((a0 + a1) + (a2 + a3));
+    y[r] = (beta == 0.0) ? v : v + beta * y[r];
+}
+// y[c] = alpha * sum_r M[r + c*ld] x[r] + beta * y[c]: one warp per column
+__global__ void __launch_bounds__(256) gemv_t_kernel(int m, int ncols, double alpha, const double* __restrict__ M, int64_t ld,
+                                                     const double* __restrict__ x, double beta, double* __restrict__ y) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= ncols) return;
+    const int lane = threadIdx.x & 31;
+    const double* col = M + (int64_t)c * ld;
+    double a0 = 0, a1 = 0;
+    int r = lane;
+    for (; r + 32 < m; r += 64) { a0 += col[r] * x[r]; a1 += col[r + 32] * x[r + 32]; }
+    if (r < m) a0 += col[r] * x[r];
+    double a = a0 + a1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) y[c] = (beta == 0.0) ? alpha * a : alpha * a + beta * y[c];
+}
+
 __global__ void pad_vector_kernel(double* dst, int N, const double* src, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t b = blockIdx.y;
@@ -161,6 +197,15 @@ int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int col
                     int batch, int64_t strideM, int64_t strideV, int64_t strideOut) {
     if (cols <= 0) return GPK_OK;
     colwise_dot<<<dim3((cols + 7) / 8, batch), 256, 0, h->stream>>>(M, ld, rows, cols, v, out, 0, square, strideM, strideV, strideOut);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_gemv(gpk_handle h, int trans, int m, int ncols, double alpha, const double* M, int64_t ld, const double* x, double beta,
+             double* y) {
+    if (m <= 0 || ncols <= 0) return GPK_OK;
+    if (!trans) gemv_n_kernel<<<(m + 127) / 128, 128, 0, h->stream>>>(m, ncols, alpha, M, ld, x, beta, y);
+    else gemv_t_kernel<<<(ncols + 7) / 8, 256, 0, h->stream>>>(m, ncols, alpha, M, ld, x, beta, y);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }

@@ -182,6 +182,12 @@ class FittedGp:
             _lib.ptr(V) if want_v else None, self.n))
         return GaussianDistribution(mean, sigma), V
 
+    @property
+    def alphaVec(self) -> np.ndarray:
+        a = np.empty(self.n)
+        self.handle.check(self.handle.lib.gpk_gp_model_get_alpha(self.handle.h, self._m, _lib.ptr(a)))
+        return a
+
     def close(self):
         if self._m:
             self.handle.lib.gpk_gp_model_destroy(self.handle.h, self._m)

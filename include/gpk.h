@@ -119,6 +119,8 @@ int gpk_gp_model_fit(gpk_handle h, const double* X, int n, int D, int64_t ldx, c
 int gpk_gp_model_from_factor(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* L,
                              int64_t ldl, const double* alpha, const double* theta, gpk_model* out);
 int gpk_gp_model_destroy(gpk_handle h, gpk_model m);
+/* alphaVec = L^t \\ (L \\ targets) of the resident model (GpPredictor.scala:121-122), n doubles. */
+int gpk_gp_model_get_alpha(gpk_handle h, gpk_model m, double* alpha);
 /* gp/regression/GpPredictor.scala:45-58 computePosterior: mean (m), sigma (m x m full if
  * want_full_cov, else only the diagonal in sigma[0..m-1]), V = L^-1 K*^t (n x m, may be NULL).
  * The sigma diagonal includes noiseVar^2 (MatrixUtils.scala:63 via GpPredictor.scala:56). */
@@ -151,6 +153,19 @@ int gpk_gp_predict_batched(gpk_handle h, int B, const double* X, int n, int D, i
                            const double* y, const double* thetas, const double* Xs, int ms, int64_t ldxs,
                            int64_t strideXs, int has_sigma_noise, double sigma_noise, double* mean, double* var,
                            double* ll, int* info);
+
+/* ---- device-level building blocks of the multi-GPU block-column Cholesky (BASELINE.json config 5) -------------
+ * Orchestrated one process per GPU by gp_algos_b200/distributed.py (torch.distributed / NCCL panel broadcasts).
+ * All pointers are DEVICE pointers, calls are asynchronous on the handle's stream; N, m, p multiples of 128, k a
+ * multiple of 16, 16-byte aligned bases, even leading dimensions. */
+/* dA (N x N, ld N, symmetric, lower used) -> L in place (lower), dLi = L^-1 (N x N, ld N); *info_dev = failing minor or 0 */
+int gpk_potrf_inv_block_dev(gpk_handle h, double* dA, double* dLi, int N, int* info_dev);
+/* C (m x p) = alpha * P (m x k) * Q (p x k)^t + beta * C, column-major; q_lower_tri != 0: Q is lower triangular (k <= c) */
+int gpk_gemm_nt_dev(gpk_handle h, int m, int p, int k, double alpha, const double* dP, int64_t ldp, const double* dQ,
+                    int64_t ldq, double beta, double* dC, int64_t ldc, int q_lower_tri);
+/* y = alpha * op(M) x + beta * y, M m x ncols column-major; trans != 0: op(M) = M^t (y has ncols entries) */
+int gpk_gemv_dev(gpk_handle h, int trans, int m, int ncols, double alpha, const double* dM, int64_t ld, const double* dx,
+                 double beta, double* dy);
 
 /* ---- EP binary GP classification (BASELINE.json config 3) ------------------------------------------
  * gp/classification/EpParameterEstimator.scala:29-69 estimateSiteParams (+ :71-96 epMarginalLikelihood, :98-109
