@@ -86,6 +86,8 @@ def load():
         lib.gpk_potrf_inv_block_dev.argtypes = [vp, vp, vp, ci, vp]
         lib.gpk_gemm_nt_dev.argtypes = [vp, ci, ci, ci, cd, vp, _i64, vp, _i64, cd, vp, _i64, ci]
         lib.gpk_gemv_dev.argtypes = [vp, ci, ci, ci, cd, vp, _i64, vp, cd, vp]
+        lib.gpk_add_diag_dev.argtypes = [vp, vp, _i64, ci, cd]
+        lib.gpk_sum_log_diag_dev.argtypes = [vp, vp, _i64, ci, vp, ci]
         lib.gpk_ep_fit.argtypes = [vp, vp, ci, _i64, vp, cd, ci, ci, ci, vp, vp, vp, vp, _i64, vp, vp, vp, vp]
         lib.gpk_ep_classify.argtypes = [vp, vp, ci, _i64, vp, ci, _i64, vp, vp, vp, vp, _i64, vp, vp, vp]
         lib.gpk_gp_nll_grad_batched.argtypes = [vp, ci, vp, ci, ci, _i64, _i64, vp, vp, ci, cd, ci, vp, vp, vp]

@@ -348,4 +348,14 @@ int gpk_gemv_dev(gpk_handle h, int trans, int m, int ncols, double alpha, const 
     return gpk_gemv(h, trans, m, ncols, alpha, dM, ld, dx, beta, dy);
 }
 
+int gpk_add_diag_dev(gpk_handle h, double* dA, int64_t ld, int n, double value) {
+    if (!h || !dA || n < 0 || ld < n) return gpk_set_error(h, GPK_EINVAL, "gpk_add_diag_dev: bad arguments");
+    return gpk_add_diag(h, dA, ld, n, value);
+}
+
+int gpk_sum_log_diag_dev(gpk_handle h, const double* dA, int64_t ld, int n, double* out_dev, int accumulate) {
+    if (!h || !dA || !out_dev || n < 0 || ld < n) return gpk_set_error(h, GPK_EINVAL, "gpk_sum_log_diag_dev: bad arguments");
+    return gpk_sum_log_diag(h, dA, ld, n, out_dev, accumulate);
+}
+
 }  // extern "C"

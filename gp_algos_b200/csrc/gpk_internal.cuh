@@ -31,7 +31,7 @@ struct gpk_handle_s {
     char err[512];
 };
 
-enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7, ARENA_PP = 8, ARENA_INFO = 9, GPK_NARENA = 12 };
+enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7, ARENA_PP = 8, ARENA_INFO = 9, ARENA_GEMV = 10, GPK_NARENA = 12 };
 
 int gpk_set_error(gpk_handle h, int status, const char* fmt, ...);
 // returns device pointer to at least `bytes` bytes in arena `which` (contents undefined after growth)
@@ -159,6 +159,8 @@ int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int col
 // y = alpha * op(M) x + beta * y for a column-major m x ncols matrix (trans: y has ncols entries)
 int gpk_gemv(gpk_handle h, int trans, int m, int ncols, double alpha, const double* M, int64_t ld, const double* x, double beta,
              double* y);
+int gpk_add_diag(gpk_handle h, double* A, int64_t ld, int n, double v);                                       // A_ii += v
+int gpk_sum_log_diag(gpk_handle h, const double* A, int64_t ld, int n, double* out, int accumulate);         // sum_i log A_ii
 // out[b*strideOut] = -0.5*y.alpha - sum_{i<n} log(diag_i(A)) - 0.5*n*log(2 pi)   (GpPredictor.scala:144-149)
 int gpk_loglik(gpk_handle h, const double* A, int N, int n, const double* y, const double* alpha, double* out, int batch = 1,
                int64_t strideOut = 0);

@@ -96,24 +96,53 @@ __global__ void __launch_bounds__(256) loglik_kernel(const double* __restrict__ 
     if (threadIdx.x == 0) out[b * strideOut] = -0.5 * sd[0] - sl[0] - 0.5 * n * log(2.0 * 3.14159265358979323846);
 }
 
-// y = alpha * M x + beta * y, M m x ncols column-major: one thread per row (coalesced over rows)
-__global__ void __launch_bounds__(128) gemv_n_kernel(int m, int ncols, double alpha, const double* __restrict__ M, int64_t ld,
-                                                     const double* __restrict__ x, double beta, double* __restrict__ y) {
+// y = alpha * M x + beta * y, M m x ncols column-major.  Split over column chunks (grid.y) so that a tall panel
+// (m = 32768, ncols = 1024) keeps ~8 MB of loads in flight; partial sums go to scratch and are added in chunk order
+// (deterministic, no floating-point atomics).  One thread per row, coalesced over rows.
+__global__ void __launch_bounds__(128) gemv_n_partial(int m, int ncols, int cchunk, const double* __restrict__ M, int64_t ld,
+                                                      const double* __restrict__ x, double* __restrict__ partial) {
     const int r = blockIdx.x * 128 + threadIdx.x;
     if (r >= m) return;
-    const double* p = M + r;
+    const int c0 = blockIdx.y * cchunk, c1 = min(c0 + cchunk, ncols);
+    const double* p = M + r + (int64_t)c0 * ld;
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    int c = 0;
-    for (; c + 3 < ncols; c += 4) {
+    int c = c0;
+    for (; c + 3 < c1; c += 4) {
         a0 += p[0] * x[c];
         a1 += p[ld] * x[c + 1];
         a2 += p[2 * ld] * x[c + 2];
         a3 += p[3 * ld] * x[c + 3];
         p += 4 * ld;
     }
-    for (; c < ncols; ++c) { a0 += p[0] * x[c]; p += ld; }
-    const double v = alpha * ((a0 + a1) + (a2 + a3));
-    y[r] = (beta == 0.0) ? v : v + beta * y[r];
+    for (; c < c1; ++c) { a0 += p[0] * x[c]; p += ld; }
+    partial[(int64_t)blockIdx.y * m + r] = (a0 + a1) + (a2 + a3);
+}
+__global__ void gemv_n_finish(int m, int nchunks, double alpha, const double* __restrict__ partial, double beta,
+                              double* __restrict__ y) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    double acc = 0.0;
+    for (int ch = 0; ch < nchunks; ++ch) acc += partial[(int64_t)ch * m + r];
+    y[r] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[r];
+}
+// A[i + i*ld] += v for i < n
+__global__ void add_diag_kernel(double* A, int64_t ld, int n, double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[i + (int64_t)i * ld] += v;
+}
+// out[0] (+)= sum_{i<n} log A[i + i*ld]   (one CTA, fixed summation order)
+__global__ void __launch_bounds__(256) sum_log_diag_kernel(const double* __restrict__ A, int64_t ld, int n, double* out,
+                                                           int accumulate) {
+    __shared__ double sl[256];
+    double l = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) l += log(A[i + (int64_t)i * ld]);
+    sl[threadIdx.x] = l;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sl[threadIdx.x] += sl[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = accumulate ? out[0] + sl[0] : sl[0];
 }
 // y[c] = alpha * sum_r M[r + c*ld] x[r] + beta * y[c]: one warp per column
 __global__ void __launch_bounds__(256) gemv_t_kernel(int m, int ncols, double alpha, const double* __restrict__ M, int64_t ld,
@@ -204,8 +233,33 @@ int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int col
 int gpk_gemv(gpk_handle h, int trans, int m, int ncols, double alpha, const double* M, int64_t ld, const double* x, double beta,
              double* y) {
     if (m <= 0 || ncols <= 0) return GPK_OK;
-    if (!trans) gemv_n_kernel<<<(m + 127) / 128, 128, 0, h->stream>>>(m, ncols, alpha, M, ld, x, beta, y);
-    else gemv_t_kernel<<<(ncols + 7) / 8, 256, 0, h->stream>>>(m, ncols, alpha, M, ld, x, beta, y);
+    if (!trans) {
+        const int rblocks = (m + 127) / 128;
+        int nch = (4 * 148 + rblocks - 1) / rblocks;               // ~4 CTAs per SM in total
+        nch = max(1, min(nch, (ncols + 63) / 64));                 // at least 64 columns per chunk
+        const int cchunk = ((ncols + nch - 1) / nch + 3) & ~3;
+        nch = (ncols + cchunk - 1) / cchunk;
+        double* partial = (double*)gpk_arena(h, ARENA_GEMV, (size_t)nch * m * sizeof(double));
+        if (!partial) return GPK_ENOMEM;
+        gemv_n_partial<<<dim3(rblocks, nch), 128, 0, h->stream>>>(m, ncols, cchunk, M, ld, x, partial);
+        GPK_LAUNCH_CHECK(h);
+        gemv_n_finish<<<(m + 255) / 256, 256, 0, h->stream>>>(m, nch, alpha, partial, beta, y);
+    } else {
+        gemv_t_kernel<<<(ncols + 7) / 8, 256, 0, h->stream>>>(m, ncols, alpha, M, ld, x, beta, y);
+    }
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_add_diag(gpk_handle h, double* A, int64_t ld, int n, double v) {
+    if (n <= 0) return GPK_OK;
+    add_diag_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(A, ld, n, v);
+    GPK_LAUNCH_CHECK(h);
+    return GPK_OK;
+}
+
+int gpk_sum_log_diag(gpk_handle h, const double* A, int64_t ld, int n, double* out, int accumulate) {
+    sum_log_diag_kernel<<<1, 256, 0, h->stream>>>(A, ld, n, out, accumulate);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }

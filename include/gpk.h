@@ -167,6 +167,11 @@ int gpk_gemm_nt_dev(gpk_handle h, int m, int p, int k, double alpha, const doubl
 int gpk_gemv_dev(gpk_handle h, int trans, int m, int ncols, double alpha, const double* dM, int64_t ld, const double* dx,
                  double beta, double* dy);
 
+/* dA[i + i*ld] += value for i < n (the noiseVar^2 [sameIndex] term of KernelRequisites.scala:69 on a diagonal block) */
+int gpk_add_diag_dev(gpk_handle h, double* dA, int64_t ld, int n, double value);
+/* out_dev[0] (+)= sum_{i<n} log dA[i + i*ld]: the sum_i log L_ii term of GpPredictor.scala:147 for one diagonal block */
+int gpk_sum_log_diag_dev(gpk_handle h, const double* dA, int64_t ld, int n, double* out_dev, int accumulate);
+
 /* ---- EP binary GP classification (BASELINE.json config 3) ------------------------------------------
  * gp/classification/EpParameterEstimator.scala:29-69 estimateSiteParams (+ :71-96 epMarginalLikelihood, :98-109
  * marginalMoments, :187-202 AvgBasedStopCriterion).  K: n x n symmetric kernel matrix (the reference is handed a

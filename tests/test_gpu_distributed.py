@@ -1,0 +1,66 @@
+"""GPU: the large-GP solver (gp_algos_b200/distributed.py, BASELINE.json config 5) through libgpk's device-level blocks,
+against the oracle.  1 x 1 grid in-process; 2 GPUs (when the box has them) through torchrun + NCCL."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n,nb,sigma", [(1000, 256, None), (1536, 512, 0.05), (640, 128, None)])
+def test_single_gpu_block_cholesky_matches_oracle(n, nb, sigma):
+    from oracle import gp_oracle as orc
+    from gp_algos_b200.distributed import DistributedGp
+    X, y, theta = orc.make_c2(n=n, D=8, seed=21)
+    solver = DistributedGp(nb=nb, device=0)
+    fit = solver.fit(X, y, theta, sigmaNoise=sigma)
+    L_o, alpha_o = orc.fast_precompute(X, y, theta, sigma)
+    ll_o = orc.fast_loglik(alpha_o, L_o, y)
+    assert abs(fit.logLikelihood - ll_o) <= 1e-9 * abs(ll_o)
+    assert np.allclose(fit.alphaVec, alpha_o, rtol=1e-9, atol=1e-9 * np.abs(alpha_o).max())
+    L = solver.gather_factor()
+    K = orc.fast_build_kernel_matrix(X, theta)
+    if sigma is not None:
+        K[np.diag_indices_from(K)] += sigma
+    assert np.linalg.norm(K - L @ L.T) <= 8 * n * np.finfo(float).eps * np.linalg.norm(K)      # backward-error bound
+    assert np.linalg.norm(L - L_o) <= 1e-9 * np.linalg.norm(L_o)
+    if sigma is None:
+        assert solver.residual(y, fit.alphaVec) < 1e-10
+
+
+def test_not_positive_definite_is_reported_with_its_minor():
+    from oracle import gp_oracle as orc
+    import gp_algos_b200 as gp
+    from gp_algos_b200.distributed import DistributedGp
+    X, y, theta = orc.make_c2(n=512, D=8, seed=22)
+    import scipy.linalg.lapack as lp
+    K = orc.fast_build_kernel_matrix(X, theta)
+    K[np.diag_indices_from(K)] += -0.5            # Option sigmaNoise is added un-squared (GpPredictor.scala:116): K - 0.5 I is indefinite
+    _, info = lp.dpotrf(K, lower=1)
+    assert info > 0
+    solver = DistributedGp(nb=128, device=0)
+    with pytest.raises(gp.NotPositiveDefiniteError) as e:
+        solver.fit(X, y, theta, sigmaNoise=-0.5)
+    assert e.value.minor == info
+
+
+def test_two_gpus_nccl_matches_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    outs = {}
+    for nproc, grid in ((1, "1x1"), (2, "2x1"), (2, "1x2")):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+               "--master-port", "29731", os.path.join(ROOT, "tools", "bench_c5.py"), "--n", "5000", "--nb", "256", "--grid", grid,
+               "--reps", "1"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[grid] = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        assert outs[grid]["residual_Kalpha_minus_y_over_y"] < 1e-10
+    for grid in ("2x1", "1x2"):
+        assert abs(outs[grid]["ll"] - outs["1x1"]["ll"]) <= 1e-11 * abs(outs["1x1"]["ll"])
