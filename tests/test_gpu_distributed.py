@@ -56,7 +56,7 @@ def test_two_gpus_nccl_matches_single_gpu():
     outs = {}
     for nproc, grid in ((1, "1x1"), (2, "2x1"), (2, "1x2")):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
-               "--master-port", "29731", os.path.join(ROOT, "tools", "bench_c5.py"), "--n", "5000", "--nb", "256", "--grid", grid,
+               "--master-port", "29731", os.path.join(ROOT, "tools", "bench_c5.py"), "--size", "5000", "--nb", "256", "--grid", grid,
                "--reps", "1"]
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
         assert r.returncode == 0, r.stderr[-2000:]

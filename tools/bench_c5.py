@@ -1,6 +1,6 @@
 """BASELINE.json config 5: one GP of n = 65536, D = 8 -- K build + 2-D block-cyclic FP64 Cholesky + alpha solves on N GPUs.
 
-    python tools/bench_c5.py [--n 65536] [--nb 1024] [--grid 4x2] [--reps 2]                      (1 GPU)
+    python tools/bench_c5.py [--size 65536] [--nb 1024] [--grid 4x2] [--reps 2]                      (1 GPU)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_c5.py ...
 
 Timing: CUDA events on each rank's stream around build + factor + solves, after a barrier; the reported time is the MAX
@@ -25,7 +25,7 @@ def synth(n, D=8, seed=5):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--size", dest="n", type=int, default=65536)
     ap.add_argument("--nb", type=int, default=1024)
     ap.add_argument("--grid", type=str, default="")
     ap.add_argument("--reps", type=int, default=2)
