@@ -58,11 +58,12 @@ class Vec(NamedTuple):
 # grid arithmetic (pure host logic, covered by the CPU tests)
 # ----------------------------------------------------------------------------------------------------------------
 def choose_grid(world: int) -> tuple[int, int]:
-    """Pr x Pc with Pr * Pc == world, as square as possible, Pr >= Pc (the panel solve is split over Pr ranks)."""
-    pc = int(math.isqrt(world))
-    while world % pc:
-        pc -= 1
-    return world // pc, pc
+    """Pr x Pc with Pr * Pc == world, as square as possible, Pr <= Pc: fewer process rows keep each rank's trailing-update
+    GEMMs tall (measured on 8 B200, n = 65536: 2x4 0.480 s, 4x2 0.496 s; on 2: 1x2 1.54 s, 2x1 1.61 s)."""
+    pr = int(math.isqrt(world))
+    while world % pr:
+        pr -= 1
+    return pr, world // pr
 
 
 def first_at_least(g: int, q: int, P: int) -> int:

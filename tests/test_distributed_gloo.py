@@ -17,7 +17,7 @@ from gp_algos_b200.distributed import (BlockCyclicGrid, DistributedGp, Mat, Vec,
 
 
 def test_grid_arithmetic():
-    assert choose_grid(1) == (1, 1) and choose_grid(2) == (2, 1) and choose_grid(4) == (2, 2) and choose_grid(8) == (4, 2)
+    assert choose_grid(1) == (1, 1) and choose_grid(2) == (1, 2) and choose_grid(4) == (2, 2) and choose_grid(8) == (2, 4)
     for P in (1, 2, 3, 4):
         for q in range(P):
             for g in range(0, 9):
