@@ -8,7 +8,9 @@ and error behaviour), used by the parity tests and the benchmark:
     utils.MatrixUtils       ->  gp_algos_b200.matrix_utils       (buildKernelMatrix, forwardSolve, ...)
     gp.regression.GpPredictor -> gp_algos_b200.gp_predictor      (GpPredictor, PredictionInput, ...)
     gp.classification.*      ->  gp_algos_b200.ep_classification (EpParameterEstimator, GpClassifier, ...)
-    (batched independent GPs and their rank sharding: gp_algos_b200.batched)
+    gp.optimization.GPOptimizer -> gp_algos_b200.gp_optimizer    (GP-UCB inner loop on a resident model)
+    (batched independent GPs and their rank sharding: gp_algos_b200.batched;
+     one large GP over a 2-D block-cyclic GPU grid: gp_algos_b200.distributed)
 
 There is no CPU fallback: importing works anywhere, but every numeric call raises if libgpk.so or a
 CUDA device is missing.
@@ -18,7 +20,9 @@ from .gp_predictor import GpPredictor, PredictionInput, PredictionTrainingInput,
 from . import matrix_utils as MatrixUtils  # noqa: F401
 from . import batched  # noqa: F401
 from .ep_classification import (EpParameterEstimator, GpClassifier, MarginalLikelihoodEvaluator, SiteParams,  # noqa: F401
-                                AvgBasedStopCriterion, FixedSweeps, ClassifierInput, AfterEstimationClassifierInput)
+                                AvgBasedStopCriterion, FixedSweeps, ClassifierInput, AfterEstimationClassifierInput,
+                                HyperParameterOptimInput)
+from .gp_optimizer import GPOptimizer, GPOInput, BreezeLbfgsOptimizer, ucb_with_gradient  # noqa: F401
 from ._lib import GpkError, NotPositiveDefiniteError, MatrixNotSymmetricError, lib_path  # noqa: F401
 
 __all__ = ["GaussianRbfKernel", "GaussianRbfParams", "GpPredictor", "PredictionInput", "PredictionTrainingInput",

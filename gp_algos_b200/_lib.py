@@ -82,6 +82,7 @@ def load():
         lib.gpk_gp_model_destroy.argtypes = [vp, vp]
         lib.gpk_gp_model_get_alpha.argtypes = [vp, vp, vp]
         lib.gpk_gp_model_predict.argtypes = [vp, vp, vp, ci, _i64, ci, vp, vp, _i64, vp, _i64]
+        lib.gpk_gp_model_ucb.argtypes = [vp, vp, vp, ci, _i64, cd, vp, vp, _i64, vp, vp]
         lib.gpk_gp_predict.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, _i64, vp, ci, cd, vp, vp, _i64, vp]
         lib.gpk_potrf_inv_block_dev.argtypes = [vp, vp, vp, ci, vp]
         lib.gpk_gemm_nt_dev.argtypes = [vp, ci, ci, ci, cd, vp, _i64, vp, _i64, cd, vp, _i64, ci]
@@ -90,6 +91,8 @@ def load():
         lib.gpk_sum_log_diag_dev.argtypes = [vp, vp, _i64, ci, vp, ci]
         lib.gpk_ep_fit.argtypes = [vp, vp, ci, _i64, vp, cd, ci, ci, ci, vp, vp, vp, vp, _i64, vp, vp, vp, vp]
         lib.gpk_ep_classify.argtypes = [vp, vp, ci, _i64, vp, ci, _i64, vp, vp, vp, vp, _i64, vp, vp, vp]
+        lib.gpk_ep_nll_grad.argtypes = [vp, vp, ci, ci, _i64, vp, vp, cd, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+        lib.gpk_ep_grad_from_factor.argtypes = [vp, vp, ci, ci, _i64, vp, vp, _i64, vp, vp, vp, _i64, ci, vp]
         lib.gpk_gp_nll_grad_batched.argtypes = [vp, ci, vp, ci, ci, _i64, _i64, vp, vp, ci, cd, ci, vp, vp, vp]
         lib.gpk_gp_nll_grad_batched_dev.argtypes = [vp, ci, vp, ci, ci, _i64, _i64, vp, vp, ci, cd, ci, vp, vp]
         lib.gpk_gp_predict_batched.argtypes = [vp, ci, vp, ci, ci, _i64, _i64, vp, vp, vp, ci, _i64, _i64, ci, cd, vp, vp, vp, vp]

@@ -130,6 +130,43 @@ int nll_grad_core(gpk_handle h, int B, const double* dX, int n, int D, int64_t l
     return GPK_OK;
 }
 
+
+// GPOptimizer.scala:93-103: for candidate c and input dimension d (one CTA each)
+//   G_id   = ((x_d - x_id) * 1/l_d^2) * (-k(x, x_i))                       KernelRequisites.scala:99-107, afterFirstArg
+//   dmean  = sum_i G_id alpha_i                                            testTrainDerMtx * alphaVec
+//   dvar   = 0 - 2 sum_i G_id u_i,  u = L^-t (L^-1 k*)                     derAfterVarFirst(x,x) = 0; (L^-1 G)^t v = G^t L^-t v
+//   grad   = dmean + dvar * k / (2 sqrt(sigma))
+__global__ void __launch_bounds__(256) ucb_grad_kernel(const double* __restrict__ KsT, const double* __restrict__ U, int N, int n,
+                                                       const double* __restrict__ X, const double* __restrict__ Xs, int ms,
+                                                       const double* __restrict__ alpha, const double* __restrict__ colsq,
+                                                       const double* __restrict__ mean, CovParams cp, double kparam,
+                                                       double* __restrict__ grad, double* __restrict__ ucb, double* __restrict__ var) {
+    __shared__ double sa[256], sb[256];
+    const int c = blockIdx.x, d = blockIdx.y;
+    const double xd = Xs[c + (int64_t)d * ms], inv = cp.inv_ls2[d];
+    const double* ks = KsT + (int64_t)c * N;
+    const double* u = U + (int64_t)c * N;
+    const double* xcol = X + (int64_t)d * n;
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double g = ((xd - xcol[i]) * inv) * (-ks[i]);
+        a += g * alpha[i];
+        b += g * u[i];
+    }
+    sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double sigma = (cp.sf2 + cp.sn2) - colsq[c];       // k(x,x) incl. the i==j noise term (MatrixUtils.scala:63) - v^t v
+        const double coeff = kparam / (2 * sqrt(sigma));
+        grad[c + (int64_t)d * ms] = sa[0] + (0.0 - 2.0 * sb[0]) * coeff;
+        if (d == 0) { ucb[c] = mean[c] + kparam * sqrt(sigma); var[c] = sigma; }
+    }
+}
+
 }  // namespace
 
 struct gpk_model_s {
@@ -412,6 +449,58 @@ int gpk_gp_model_predict(gpk_handle h, gpk_model m, const double* Xs, int ms, in
         for (int i = 0; i < ms; ++i) sigma[i] = kss - sigma[i];
     }
     return GPK_OK;
+}
+
+// gp/optimization/GPOptimizer.scala:82-109 maximizeUCB: the objective handed to the gradient optimiser, for ms candidate
+// points at once against a resident model (the reference calls computePosterior + two n x D derivative matrices + an
+// n x n x D product per candidate, and re-inverts L once per restart, GPOptimizer.scala:85).
+int gpk_gp_model_ucb(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_t ldxs, double k_param, double* ucb, double* grad,
+                     int64_t ldg, double* mean, double* var) {
+    if (!h || !m || !Xs || !ucb || ms <= 0 || ldxs < ms || (grad && ldg < ms))
+        return gpk_set_error(h, GPK_EINVAL, "gpk_gp_model_ucb: bad dimensions");
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    const int n = m->n, N = m->N, D = m->D, M = gpk_pad(ms);
+    const CovParams& cp = m->pp.cp;
+    ARENA_OR_FAIL(dXs, double*, h, ARENA_X, (size_t)ms * D * sizeof(double));
+    // KsT, V, U (N x M each), mean, colsq, ucb, var (M each), grad (ms x D)
+    ARENA_OR_FAIL(buf, double*, h, ARENA_IO2, ((size_t)3 * N * M + 4 * M + (size_t)ms * D) * sizeof(double));
+    double* dKsT = buf;
+    double* dV = dKsT + (size_t)N * M;
+    double* dU = dV + (size_t)N * M;
+    double* dMean = dU + (size_t)N * M;
+    double* dSq = dMean + M;
+    double* dUcb = dSq + M;
+    double* dVar = dUcb + M;
+    double* dGrad = dVar + M;
+    int rc = gpk_upload_matrix(h, dXs, Xs, ms, D, ldxs);
+    if (rc) return rc;
+    rc = gpk_cov_cross(h, m->X, n, n, dXs, ms, ms, cp, dKsT, N, N, M);          // k* (GpPredictor.scala:53)
+    if (rc) return rc;
+    rc = gpk_colwise_dot(h, dKsT, N, N, ms, m->alpha, dMean, 0);                 // mean (GpPredictor.scala:54)
+    if (rc) return rc;
+    GemmDesc g = gemm_desc();                                                    // V = L^-1 K*^t (GpPredictor.scala:55)
+    g.P = dKsT; g.ldp = N; g.p_kcontig = 1;
+    g.Q = m->Li; g.ldq = N; g.q_kcontig = 0;
+    g.D = dV; g.ldd = N; g.R = M; g.S = N; g.K = N; g.ke_s = 1; g.heavy_last = 1;
+    rc = gpk_gemm(h, g);
+    if (rc) return rc;
+    rc = gpk_colwise_dot(h, dV, N, N, ms, nullptr, dSq, 1);                      // v^t v
+    if (rc) return rc;
+    g = gemm_desc();                                                             // U = L^-t V: U(i,c) = sum_{k>=i} Li(k,i) V(k,c)
+    g.P = dV; g.ldp = N; g.p_kcontig = 1;
+    g.Q = m->Li; g.ldq = N; g.q_kcontig = 1;
+    g.D = dU; g.ldd = N; g.R = M; g.S = N; g.K = N; g.kb_s = 1;
+    rc = gpk_gemm(h, g);
+    if (rc) return rc;
+    ucb_grad_kernel<<<dim3(ms, D), 256, 0, h->stream>>>(dKsT, dU, N, n, m->X, dXs, ms, m->alpha, dSq, dMean, cp, k_param, dGrad, dUcb,
+                                                        dVar);
+    GPK_LAUNCH_CHECK(h);
+    GPK_CUDA(h, cudaMemcpyAsync(ucb, dUcb, (size_t)ms * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (mean) GPK_CUDA(h, cudaMemcpyAsync(mean, dMean, (size_t)ms * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (var) GPK_CUDA(h, cudaMemcpyAsync(var, dVar, (size_t)ms * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (grad) GPK_CUDA(h, cudaMemcpy2DAsync(grad, (size_t)ldg * sizeof(double), dGrad, (size_t)ms * sizeof(double),
+                                            (size_t)ms * sizeof(double), (size_t)D, cudaMemcpyDeviceToHost, h->stream));
+    return gpk_synchronize(h);
 }
 
 int gpk_gp_predict(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y, const double* Xs, int ms,

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const GradArgs a) {
     __shared__ double red[8];
     const int64_t pb = blockIdx.y;
     const CovParams& cp = a.pp ? a.pp[pb].cp : a.cp;
-    const double* Kinv = a.Kinv + pb * (int64_t)a.N * a.N;
+    const double* Kinv = a.Kinv ? a.Kinv + pb * (int64_t)a.N * a.N : nullptr;   // nullptr: W = alpha alpha^t only
     const double* X = a.X + pb * a.strideX;
     const double* alpha = a.alpha + pb * a.N;
     const int D = cp.D;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const GradArgs a) {
         for (int b = 0; b < 8; ++b) {
             const int gj = j0 + ty + 8 * b;
             const double aj = (gj < a.n) ? alpha[gj] : 0.0;
-            const double2 kv = *reinterpret_cast<const double2*>(Kinv + gi0 + (int64_t)gj * a.N);
+            const double2 kv = Kinv ? *reinterpret_cast<const double2*>(Kinv + gi0 + (int64_t)gj * a.N) : make_double2(0.0, 0.0);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int gi = gi0 + q;

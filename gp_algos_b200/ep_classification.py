@@ -117,12 +117,58 @@ class GpClassifier:
         return prob
 
 
-class MarginalLikelihoodEvaluator:
-    """MarginalLikelihoodEvaluator.scala:13 -- the K-build + EP + logZ entry points (:18-31).  The hyper-parameter
-    gradient (:33-66) is a SURVEY.md 8(f) "next" row and is not lowered yet."""
+@dataclass
+class HyperParameterOptimInput:
+    """MarginalLikelihoodEvaluator.scala:88-89."""
+    siteParams: SiteParams
+    lowerTriangular: np.ndarray
+    kernelMatrix: np.ndarray
+    trainInput: np.ndarray
 
-    def __init__(self, stopCriterion, kernelFunc, handle=None):
+
+class MarginalLikelihoodEvaluator:
+    """MarginalLikelihoodEvaluator.scala:13 -- K build + EP + logZ (:18-31) and the hyper-parameter gradient (:33-66,
+    reproduced as compiled: rMatrix = b b^t, see include/gpk.h gpk_ep_nll_grad)."""
+
+    def __init__(self, stopCriterion, kernelFunc, handle=None, keep_linebreak_quirk: bool = True):
         self.stopCriterion, self.kernelFunc, self._handle = stopCriterion, kernelFunc, handle
+        self.keep_quirk = keep_linebreak_quirk
+        self.sweeps = None
+        self.siteParams = None
+
+    def logLikelihood(self, trainInput, targets, hyperParams):
+        """-> (logZ, gradient[hyperParametersNum])   (MarginalLikelihoodEvaluator.scala:33-45), one fused device call."""
+        h = self._handle or _lib.default_handle()
+        kf = self.kernelFunc.changeHyperParams(hyperParams)
+        X = _lib.fmat(trainInput)
+        t = np.ascontiguousarray(targets, dtype=np.int32)
+        theta = np.ascontiguousarray(kf.theta, dtype=np.float64)
+        n, D = X.shape
+        if t.shape[0] != n:
+            raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, "requirement failed")
+        eps, fixed, mx = _stop_args(self.stopCriterion)
+        P = kf.hyperParametersNum
+        grad = np.empty(P); tau = np.empty(n); nu = np.empty(n)
+        logz = C.c_double(); sw = C.c_int()
+        h.check(h.lib.gpk_ep_nll_grad(h.h, _lib.ptr(X), n, D, n, _lib.ptr(theta), t.ctypes.data_as(C.c_void_p), eps, fixed, mx,
+                                      int(self.keep_quirk), P, C.addressof(logz), _lib.ptr(grad), _lib.ptr(tau), _lib.ptr(nu),
+                                      C.addressof(sw)))
+        self.sweeps, self.siteParams = sw.value, SiteParams(tau, nu, logz.value)
+        return logz.value, grad
+
+    def logLikelihoodDerivativesAfterHyperParams(self, optimInput: "HyperParameterOptimInput", kernelFun) -> np.ndarray:
+        """MarginalLikelihoodEvaluator.scala:47-66 from a finished EP run (siteParams, L, K, X)."""
+        h = self._handle or _lib.default_handle()
+        X = _lib.fmat(optimInput.trainInput); K = _lib.fmat(optimInput.kernelMatrix); L = _lib.fmat(optimInput.lowerTriangular)
+        tau = np.ascontiguousarray(optimInput.siteParams.tauSiteParams, dtype=np.float64)
+        nu = np.ascontiguousarray(optimInput.siteParams.niSiteParams, dtype=np.float64)
+        theta = np.ascontiguousarray(kernelFun.theta, dtype=np.float64)
+        n, D = X.shape
+        P = kernelFun.hyperParametersNum
+        grad = np.empty(P)
+        h.check(h.lib.gpk_ep_grad_from_factor(h.h, _lib.ptr(X), n, D, n, _lib.ptr(theta), _lib.ptr(K), n, _lib.ptr(tau), _lib.ptr(nu),
+                                              _lib.ptr(L), n, P, _lib.ptr(grad)))
+        return grad
 
     def logLikelihoodWithKernelMatrixPassed(self, kernelMatrix, targets) -> float:
         site, _ = EpParameterEstimator(kernelMatrix, targets, self.stopCriterion, self._handle).estimateSiteParams

@@ -126,6 +126,13 @@ int gpk_gp_model_get_alpha(gpk_handle h, gpk_model m, double* alpha);
  * The sigma diagonal includes noiseVar^2 (MatrixUtils.scala:63 via GpPredictor.scala:56). */
 int gpk_gp_model_predict(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_t ldxs,
                          int want_full_cov, double* mean, double* sigma, int64_t lds, double* V, int64_t ldv);
+/* gp/optimization/GPOptimizer.scala:82-109 maximizeUCB's objective for ms candidate points (rows of Xs) at once:
+ * ucb[i] = mean_i + k_param sqrt(sigma_i) and grad[i + d*ldg] = d ucb_i / d x_d
+ *        = (dKs/dx) alpha + (0 - 2 (L^-1 dKs^t/dx)^t v) k_param / (2 sqrt(sigma_i)), Ks = k(x, X), v = L^-1 Ks^t
+ *          (KernelRequisites.scala:99-107),
+ * with mean/sigma from computePosterior (sigma includes noiseVar^2).  mean, var, grad may be NULL. */
+int gpk_gp_model_ucb(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_t ldxs, double k_param, double* ucb,
+                     double* grad, int64_t ldg, double* mean, double* var);
 /* gp/regression/GpPredictor.scala:24-43 predict: fit + computePosterior (+ sigma_noise * I) + ll. */
 int gpk_gp_predict(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y,
                    const double* Xs, int ms, int64_t ldxs, const double* theta, int has_sigma_noise,
@@ -190,6 +197,22 @@ int gpk_ep_fit(gpk_handle h, const double* K, int n, int64_t ldk, const int* tar
 int gpk_ep_classify(gpk_handle h, const double* K, int n, int64_t ldk, const double* Ks, int m, int64_t ldks,
                     const double* kss_diag, const double* tau, const double* nu, const double* L, int64_t ldl,
                     double* prob, double* fmean, double* fvar);
+
+/* gp/classification/MarginalLikelihoodEvaluator.scala:33-45 logLikelihood(trainInput, targets, hyperParams) -> (logZ,
+ * gradient): K = buildKernelMatrix(kernel(theta), X) is built on the device, EP runs to the stop rule (arguments as
+ * gpk_ep_fit), then the hyper-parameter gradient of :47-66 AS COMPILED: the statement at :58 ends at the newline, so
+ * rMatrix = b b^t and grad[p] = 1/2 b^t (dK/dtheta_{p+1}) b with b = nu - (S^1/2 L)^-1 L^-t S^1/2 K nu (:53-57; the
+ * inner forward solve of Rasmussen & Williams Alg. 5.2 is absent in the reference and therefore here).  dK/dtheta is
+ * never materialised.  Outputs: logZ, grad[nparams], tau/nu[n] (may be NULL), sweeps (may be NULL). */
+int gpk_ep_nll_grad(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* theta, const int* targets,
+                    double eps, int fixed_sweeps, int max_sweeps, int keep_linebreak_quirk, int nparams, double* logZ,
+                    double* grad, double* tau, double* nu, int* sweeps);
+/* MarginalLikelihoodEvaluator.scala:47-66 logLikelihoodDerivativesAfterHyperParams(HyperParameterOptimInput(siteParams,
+ * lowerTriangular, kernelMatrix, trainInput), kernelFun): the gradient alone from a finished EP run.  K may be NULL
+ * (rebuilt from X and theta). */
+int gpk_ep_grad_from_factor(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* theta, const double* K,
+                            int64_t ldk, const double* tau, const double* nu, const double* L, int64_t ldl, int nparams,
+                            double* grad);
 
 #ifdef __cplusplus
 }

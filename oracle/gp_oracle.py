@@ -258,6 +258,37 @@ def lit_predict(X, y, Xs, theta, sigma_noise=None):
     return mean, sigma, ll.value
 
 
+def lit_kernel_gradient(theta, v1, v2, after_first_arg):
+    """KR:99-107 GaussianRbfKernel.gradient(afterFirstArg)(vec1, vec2), same association."""
+    theta = np.asarray(theta, dtype=np.float64)
+    D = len(theta) - 2
+    v1 = np.asarray(v1, dtype=np.float64); v2 = np.asarray(v2, dtype=np.float64)
+    diff = v1 - v2
+    inv = np.array([1.0 / (ls * ls) for ls in theta[1:D + 1]])
+    a1 = theta[0] * theta[0] * math.exp(-0.5 * float(np.dot(diff * inv, diff)))    # apply(vec1, vec2, sameIndex = false)
+    return (diff * inv) * (-a1) if after_first_arg else (diff * inv) * a1
+
+
+def lit_ucb_with_grad(X, L, alpha, theta, x, k_param):
+    """GPO:87-104: the objective of maximizeUCB at one test point -> (ucb, ucbDer[D], mean, sigma)."""
+    X = _f(X); L = _f(L)
+    x = np.asarray(x, dtype=np.float64)
+    n, D = X.shape
+    inversedL = lit_inv_triangular(L, is_upper=False)                                   # GPO:85
+    mean, sigma, V = lit_compute_posterior(X, x.reshape(1, D), L, alpha, theta)         # GPO:89-90
+    ucb = mean[0] + k_param * math.sqrt(sigma[0, 0])                                    # GPO:93
+    testTrain = np.zeros((D, n)); trainTest = np.zeros((n, D))
+    for i in range(n):                                                                  # GPO:111-127
+        testTrain[:, i] = lit_kernel_gradient(theta, x, X[i], True)
+        trainTest[i, :] = lit_kernel_gradient(theta, X[i], x, False)
+    derAfterMean = testTrain @ alpha                                                    # GPO:96
+    derAfterVarFirst = lit_kernel_gradient(theta, x, x, True)                           # GPO:97
+    vAfterX = inversedL @ trainTest                                                     # GPO:98
+    derAfterVar = derAfterVarFirst - (vAfterX.T @ V[:, 0]) * 2.0                        # GPO:100
+    coeff = k_param / (2 * math.sqrt(sigma[0, 0]))                                      # GPO:101
+    return ucb, derAfterMean + derAfterVar * coeff, mean[0], sigma[0, 0]                # GPO:102-103
+
+
 def pnorm(z):
     """StatsUtils.scala:17 (Breeze Gaussian(0,1).cdf) restated as 0.5*erfc(-z/sqrt 2)."""
     return _L().orc_pnorm(C.c_double(z))
@@ -293,6 +324,38 @@ def lit_ep_classify(K, Ks, Kss, tau, nu, L):
     prob = np.zeros(m); fm = np.zeros(m); fv = np.zeros(m)
     _L().orc_ep_classify(_p(K), n, _p(Ks), m, _p(Kss), _p(tau), _p(nu), _p(L), _p(prob), _p(fm), _p(fv))
     return prob, fm, fv
+
+
+def lit_ep_loglik_derivs(X, theta, K, tau, nu, L, keep_quirk=True):
+    """MLE2:47-66 logLikelihoodDerivativesAfterHyperParams, statement by statement, on the literal solves / builders.
+    keep_quirk=True reproduces the reference AS COMPILED: `val rMatrix = (bVector * bVector.t)` ends at the newline
+    (MLE2:58), the following `- backSolve(...)` line is a discarded unary-minus expression, so rMatrix = b b^t.
+    keep_quirk=False subtracts that term (what the source text seems to intend).  The missing inner forward solve of
+    R&W Alg. 5.2 (MLE2:53-56) is reproduced in both modes: it is ordinary code, not a parsing accident."""
+    X = _f(X); K = _f(K); L = _f(L)
+    tau = np.asarray(tau, dtype=np.float64); nu = np.asarray(nu, dtype=np.float64)
+    n, D = X.shape
+    st = np.sqrt(tau)                                   # MLE2:51
+    S = np.diag(st)                                     # MLE2:52
+    temp = lit_back_solve(np.asfortranarray(L.T), (S @ K) @ nu)              # MLE2:53-54  (R = lowerTriangular.t)
+    b = nu - lit_forward_solve(np.asfortranarray(S @ L), temp)               # MLE2:55-56
+    R = np.outer(b, b)                                                       # MLE2:58
+    if not keep_quirk:
+        temp1 = lit_forward_solve(L, np.asfortranarray(S))                   # MLE2:57
+        R = R - lit_back_solve(np.asfortranarray(S @ L.T), temp1)            # MLE2:59
+    g = np.zeros(D + 2)
+    for p in range(D + 2):                                                   # MLE2:60-65
+        Cm = lit_build_der_matrix(p + 1, X, theta)
+        g[p] = 0.5 * np.trace(R @ Cm)
+    return g
+
+
+def lit_ep_loglik_with_derivs(X, targets, theta, eps=0.01, fixed_sweeps=0, max_sweeps=100, keep_quirk=True):
+    """MLE2:33-45 logLikelihood -> (logZ, gradient, ep dict)."""
+    K = lit_build_kernel_matrix(X, theta)
+    o = lit_ep_estimate(K, targets, eps=eps, fixed_sweeps=fixed_sweeps, max_sweeps=max_sweeps, keep_quirk=keep_quirk)
+    g = lit_ep_loglik_derivs(X, theta, K, o["tau"], o["nu"], o["L"], keep_quirk=keep_quirk)
+    return o["logZ"], g, o
 
 
 # --------------------------------------------------------------------------------------------
@@ -482,6 +545,26 @@ def fast_ep_classify(K, Ks, Kss, tau, nu, L):
 # --------------------------------------------------------------------------------------------
 # synthetic workloads of SURVEY.md 8(d) (seeds fixed there)
 # --------------------------------------------------------------------------------------------
+def fast_ep_loglik_derivs(X, theta, K, tau, nu, L):
+    """MLE2:47-66 as compiled (rMatrix = b b^t), LAPACK solves, dK/dtheta in closed form: g_p = 1/2 b^t C_p b."""
+    import scipy.linalg as sla
+    X = np.asarray(X, dtype=np.float64)
+    n, D = X.shape
+    sf, ls, sn = theta[0], np.asarray(theta[1:D + 1]), theta[D + 1]
+    st = np.sqrt(tau)
+    temp = sla.solve_triangular(L, st * (K @ nu), lower=True, trans="T", check_finite=False)
+    b = nu - sla.solve_triangular(L, temp / st, lower=True, check_finite=False)
+    E = np.exp(-0.5 * _scaled_sqdist(X, X, ls))
+    g = np.zeros(D + 2)
+    g[0] = 0.5 * 2.0 * sf * (b @ E @ b)
+    W = E * np.outer(b, b)
+    for d in range(D):
+        diff = X[:, d][:, None] - X[:, d][None, :]
+        g[1 + d] = 0.5 * sf * sf * np.sum(W * diff * diff) / ls[d] ** 3
+    g[D + 1] = 0.5 * 2.0 * sn * (b @ b)
+    return g
+
+
 def make_c1(n=1000, m=500, seed=1):
     rng = np.random.default_rng(seed)
     x = rng.uniform(0, 10, size=(n, 1))

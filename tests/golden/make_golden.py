@@ -5,7 +5,7 @@
 
 * mu_3x3.npz        -- the 3x3 cases of the reference's src/test/scala/utils/MatrixUtilsTest.scala:24-114 with the
                        oracle's outputs (and numpy.linalg.solve/inv answers the Scala test compares against).
-* c1_small.npz, c2_small.npz, c3_small.npz, c4_small.npz
+* c1_small.npz, c2_small.npz, c3_small.npz, c3_grad_small.npz, c4_small.npz
                     -- reduced-size instances of BASELINE.json configs 1-4 (SURVEY.md 8(d) generators and seeds)
                        evaluated by the LITERAL oracle (oracle/gp_oracle.c).
 * boston_soft.npz   -- soft fixture: the reference's own shipped resources src/main/resources/boston.csv and
@@ -74,6 +74,17 @@ def c3_small(n=160, D=4, m=23):
              tau=ship["tau"], nu=ship["nu"], logZ=ship["logZ"], sweeps=ship["sweeps"], prob=p, fmean=fm, fvar=fv)
 
 
+def c3_grad_small(n=140, D=3):
+    """MarginalLikelihoodEvaluator.logLikelihood (MLE2:33-66) by the literal oracle, as compiled and with the dropped term."""
+    X, t, th = orc.make_c3(n=n, D=D, seed=31)
+    th = th.copy(); th[-1] = 0.2          # non-zero noise so that the d/d(noiseVar) component is exercised
+    lz, g, o = orc.lit_ep_loglik_with_derivs(X, t, th, eps=0.01)
+    K = orc.lit_build_kernel_matrix(X, th)
+    g_noquirk = orc.lit_ep_loglik_derivs(X, th, K, o["tau"], o["nu"], o["L"], keep_quirk=False)
+    np.savez(os.path.join(HERE, "c3_grad_small.npz"), X=X, targets=t, theta=th, logZ=lz, grad=g, grad_noquirk=g_noquirk,
+             sweeps=o["sweeps"], tau=o["tau"], nu=o["nu"])
+
+
 def c4_small(B=6, n=192, D=8, m=17):
     out = {}
     for b in range(B):
@@ -105,7 +116,7 @@ def boston_soft():
 
 
 if __name__ == "__main__":
-    mu_3x3(); c1_small(); c2_small(); c3_small(); c4_small()
+    mu_3x3(); c1_small(); c2_small(); c3_small(); c3_grad_small(); c4_small()
     if os.path.isdir(REF):
         boston_soft()
     print("golden fixtures written to", HERE)

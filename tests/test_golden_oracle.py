@@ -47,6 +47,16 @@ def test_c3_small_golden():
     assert r["sweeps"] == int(g["sweeps"])
 
 
+def test_c3_grad_small_golden():   # MarginalLikelihoodEvaluator.scala:33-66
+    g = np.load(os.path.join(G, "c3_grad_small.npz"))
+    K = orc.fast_build_kernel_matrix(g["X"], g["theta"])
+    r = orc.fast_ep_estimate(K, g["targets"], eps=0.01)
+    assert r["sweeps"] == int(g["sweeps"])
+    assert abs(r["logZ"] - float(g["logZ"])) <= 1e-9 * abs(float(g["logZ"]))
+    gf = orc.fast_ep_loglik_derivs(g["X"], g["theta"], K, r["tau"], r["nu"], r["L"])
+    assert np.allclose(gf, g["grad"], rtol=1e-9, atol=1e-9 * np.abs(g["grad"]).max())
+
+
 def test_boston_soft_fixture_pins_oracle_to_reference_outputs():
     g = np.load(os.path.join(G, "boston_soft.npz"))
     nt = int(g["ntrain"])

@@ -74,6 +74,48 @@ def test_ep_classifier_end_to_end_vs_fast_oracle():
     assert np.mean((ptrain > 0.5) == (t > 0)) > 0.85
 
 
+def test_golden_c3_grad_small():   # MarginalLikelihoodEvaluator.logLikelihood, MarginalLikelihoodEvaluator.scala:33-66
+    g = np.load(os.path.join(G, "c3_grad_small.npz"))
+    th = g["theta"]
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
+    ev = gp.MarginalLikelihoodEvaluator(gp.AvgBasedStopCriterion(0.01), kf)
+    logz, grad = ev.logLikelihood(g["X"], g["targets"], th)
+    assert ev.sweeps == int(g["sweeps"])
+    assert abs(logz - float(g["logZ"])) <= RTOL * abs(float(g["logZ"]))
+    assert close(grad, g["grad"])
+    assert close(ev.siteParams.tauSiteParams, g["tau"]) and close(ev.siteParams.niSiteParams, g["nu"])
+
+
+@pytest.mark.parametrize("n,D,sweeps,sn", [(60, 2, 2, 0.3), (200, 4, 3, 0.1), (333, 5, 2, 0.0)])
+def test_ep_hyperparameter_gradient_vs_literal_oracle(n, D, sweeps, sn):
+    X, t, th = orc.make_c3(n=n, D=D, seed=100 + n)
+    th = th.copy(); th[-1] = sn
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
+    ev = gp.MarginalLikelihoodEvaluator(gp.FixedSweeps(sweeps), kf)
+    logz, grad = ev.logLikelihood(X, t, th)
+    lz_o, g_o, o = orc.lit_ep_loglik_with_derivs(X, t, th, fixed_sweeps=sweeps)
+    assert abs(logz - lz_o) <= RTOL * abs(lz_o)
+    assert close(grad, g_o)
+    # the two-step route of the reference: estimateSiteParams, then logLikelihoodDerivativesAfterHyperParams
+    K = gp.MatrixUtils.buildKernelMatrix(kf, X)
+    site, L = gp.EpParameterEstimator(K, t, gp.FixedSweeps(sweeps)).estimateSiteParams
+    g2 = ev.logLikelihoodDerivativesAfterHyperParams(gp.HyperParameterOptimInput(site, L, K, X), kf)
+    assert close(g2, g_o)
+
+
+def test_ep_gradient_medium_vs_fast_oracle():
+    X, t, th = orc.make_c3(n=1100, D=4, seed=5)
+    th = th.copy(); th[-1] = 0.1
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
+    ev = gp.MarginalLikelihoodEvaluator(gp.AvgBasedStopCriterion(0.01), kf)
+    logz, grad = ev.logLikelihood(X, t, th)
+    K = orc.fast_build_kernel_matrix(X, th)
+    o = orc.fast_ep_estimate(K, t, eps=0.01)
+    assert ev.sweeps == o["sweeps"]
+    assert abs(logz - o["logZ"]) <= RTOL * abs(o["logZ"])
+    assert close(grad, orc.fast_ep_loglik_derivs(X, th, K, o["tau"], o["nu"], o["L"]), rtol=1e-8)
+
+
 def test_ep_requirements():
     with pytest.raises(ValueError):  # require(kernelMatrix.rows == targets.length)
         gp.EpParameterEstimator(np.eye(4), np.ones(3, dtype=np.int32), gp.FixedSweeps(1))

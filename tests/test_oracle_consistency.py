@@ -135,3 +135,21 @@ def test_ep_linebreak_quirk_switch():  # EpParameterEstimator.scala:91-92
     f = orc.lit_ep_estimate(K, t, fixed_sweeps=2, keep_quirk=False)
     extra = np.sum(0.5 * np.log(1 + q["tau"] / q["cav_tau"]) - np.log(np.diag(q["L"])))
     assert abs((f["logZ"] - q["logZ"]) - extra) <= 1e-10 * max(1.0, abs(extra))
+
+
+def test_ep_hyperparameter_gradient_literal_vs_fast_and_quirk():  # MarginalLikelihoodEvaluator.scala:47-66
+    X, t, th = orc.make_c3(n=90, D=3, seed=17)
+    th = th.copy(); th[-1] = 0.25
+    logz, g, o = orc.lit_ep_loglik_with_derivs(X, t, th, fixed_sweeps=3)
+    K = orc.lit_build_kernel_matrix(X, th)
+    gf = orc.fast_ep_loglik_derivs(X, th, K, o["tau"], o["nu"], o["L"])
+    assert np.allclose(g, gf, rtol=1e-10, atol=1e-10 * np.abs(g).max())
+    # as compiled rMatrix = b b^t, so every g_p is the quadratic form 1/2 b^t C_p b
+    st = np.sqrt(o["tau"])
+    b = o["nu"] - np.linalg.solve(np.diag(st) @ o["L"], np.linalg.solve(o["L"].T, st * (K @ o["nu"])))
+    for p in range(5):
+        Cm = orc.lit_build_der_matrix(p + 1, X, th)
+        assert abs(g[p] - 0.5 * b @ Cm @ b) <= 1e-9 * max(abs(g[p]), 1e-9 * np.abs(g).max())
+    # the discarded `- backSolve(...)` line changes the result when it is not discarded
+    g2 = orc.lit_ep_loglik_derivs(X, th, K, o["tau"], o["nu"], o["L"], keep_quirk=False)
+    assert np.abs(g2 - g).max() > 1e-3 * np.abs(g).max()
