@@ -26,6 +26,7 @@ void* gpk_arena(gpk_handle h, int which, size_t bytes) {
     if (h->arena[which]) {
         cudaStreamSynchronize(h->stream);
         for (int i = 0; i < GPK_NSIDE; ++i) cudaStreamSynchronize(h->side[i]);
+        for (int i = 0; i < 2; ++i) cudaStreamSynchronize(h->pipe[i]);
         cudaFree(h->arena[which]);
         h->arena[which] = nullptr;
         h->arena_bytes[which] = 0;
@@ -99,8 +100,17 @@ int gpk_create(gpk_handle* out, int device, void* stream) {
         return GPK_ENOMEM;
     }
     cudaMemset(h->d_info, 0, 4 * sizeof(int));
+    // side streams (off-critical-path GEMMs that are joined inside a recursion node) run one priority step above the
+    // pipelined driver's bulk streams, which take the lowest priority
+    int least = 0, greatest = 0, mainprio = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    cudaStreamGetPriority(h->stream, &mainprio);
+    // numerically lower = more urgent; [greatest, least] is e.g. [-5, 0]
+    const int sideprio = (mainprio < least && least - 1 >= greatest) ? least - 1 : least;
     for (int i = 0; i < GPK_NSIDE; ++i)
-        if (cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, 0 /* lowest */) != cudaSuccess) { delete h; return GPK_ECUDA; }
+        if (cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, sideprio) != cudaSuccess) { delete h; return GPK_ECUDA; }
+    for (int i = 0; i < 2; ++i)
+        if (cudaStreamCreateWithPriority(&h->pipe[i], cudaStreamNonBlocking, least) != cudaSuccess) { delete h; return GPK_ECUDA; }
     for (int i = 0; i < GPK_NEVENTS; ++i)
         if (cudaEventCreateWithFlags(&h->evpool[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return GPK_ECUDA; }
     *out = h;
@@ -113,6 +123,8 @@ int gpk_destroy(gpk_handle h) {
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < GPK_NSIDE; ++i)
         if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
+    for (int i = 0; i < 2; ++i)
+        if (h->pipe[i]) { cudaStreamSynchronize(h->pipe[i]); cudaStreamDestroy(h->pipe[i]); }
     for (int i = 0; i < GPK_NARENA; ++i)
         if (h->arena[i]) cudaFree(h->arena[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);

@@ -48,6 +48,17 @@ int side_min() {
     return v;
 }
 
+int pipe_nb() {      // block-column width of the pipelined driver
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPK_PIPE_NB"); v = e ? atoi(e) : 1024; if (v < NB || v % NB) v = 1024; }
+    return v;
+}
+int pipe_min() {     // smallest padded N that takes the pipelined driver (0 disables it)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPK_PIPE_MIN"); v = e ? atoi(e) : 4096; }
+    return v;
+}
+
 void set_batch(GemmDesc& g, const Ctx& c, int64_t sP, int64_t sQ, int64_t sD, int64_t sC) {
     g.batch = c.batch; g.strideP = sP; g.strideQ = sQ; g.strideD = sD; g.strideC = sC;
 }
@@ -152,13 +163,154 @@ int trtri_rec(const Ctx& c, const double* L, double* Li, double* T, int n) {
 
 }  // namespace
 
-size_t gpk_chol_scratch_doubles(int N) {
+static size_t rec_scratch_doubles(int N) {
     // sum over recursion depths of n1*n2 <= (N/2+64)^2 * (1 + 1/4 + 1/16 + ...) plus slack for uneven splits
     const size_t half = (size_t)(N / 2 + NB);
     return half * half * 3 / 2 + (size_t)N * NB;
 }
 
+size_t gpk_chol_scratch_doubles(int N) {
+    const size_t rec = rec_scratch_doubles(N);
+    const size_t pipe = rec_scratch_doubles(pipe_nb()) + (size_t)pipe_nb() * N;   // diagonal-block scratch + one row panel
+    return rec > pipe ? rec : pipe;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pipelined (look-ahead) driver for one large problem.  The recursion above leaves most SMs idle while it walks the
+// bottom of the tree (128-blocks: one CTA; 256..1024 nodes: a handful of 64x64 tiles) -- ~7 ms of the 23 ms evaluation
+// at n = 8192 (profiles/r01_launches_v3_eval.csv).  Here the matrix is cut into block columns of nbk (1024) and three
+// streams run concurrently:
+//   M  (the handle's stream, high priority) -- the serial spine: for k = 0..nt-1
+//          F_k  L_kk, L_kk^-1 = potrf_inv_rec(A_kk)                       (the recursion, on a 1024 block)
+//          P_k  L_ik = A_ik L_kk^-T for all i > k, staged in Li's (i,k) slots (free until row i is inverted)
+//          U_k(:,k+1)  block column k+1 -= L_:k L_{k+1,k}^T               (look-ahead: F_{k+1} can start at once)
+//   S  (low priority) -- the rest of trailing update k: block column k+2 first (M's next look-ahead needs it), then
+//          the lower triangle of columns >= k+3 in one SYRK launch;
+//   S2 (low priority) -- as soon as F_i is done, row i of the inverse
+//          T_i = L_{i,0:i} Li_{0:i,0:i};  Li_{i,0:i} = -Li_ii T_i          (L row i is dead once F_i has run)
+//      and its contribution to K^-1 = Li^t Li (GpPredictor.scala:67):
+//          Kinv[i,0:i] = Li_ii^t Li_{i,0:i}; Kinv[i,i] = Li_ii^t Li_ii; Kinv[0:i,0:i] += Li_{i,0:i}^t Li_{i,0:i}.
+// Same n^3 flops as the recursive path, same GEMM kernel; only the order changes, so the spine hides behind ~14 ms of
+// full-GPU GEMM work.  Hazards are argued in DESIGN.md section 4 (each block column's updates finish before its F).
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+inline cudaEvent_t next_event(gpk_handle h) { return h->evpool[h->ev_next++ % GPK_NEVENTS]; }
+
+// block column jc (rows >= its own start) -= L_{:,k} L_{jc,k}^t, L staged in Li's slots; lower tiles of the diagonal block only
+int col_update(gpk_handle h, double* A, const double* Li, int N, int bk, int sk, int bj, int sj) {
+    GemmDesc g = gemm_desc();
+    g.P = Li + bj + (int64_t)bk * N; g.ldp = N;
+    g.Q = Li + bj + (int64_t)bk * N; g.ldq = N;
+    g.D = A + bj + (int64_t)bj * N; g.ldd = N; g.Cin = g.D; g.ldc = N;
+    g.R = sj; g.S = N - bj; g.K = sk; g.alpha = -1.0; g.beta = 1.0; g.tri_out = 1;
+    return gpk_gemm(h, g);
+}
+
+}  // namespace
+
+int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev) {
+    const int nbk = pipe_nb();
+    const int nt = (N + nbk - 1) / nbk;
+    auto bs = [&](int k) { return k * nbk < N ? k * nbk : N; };
+    GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
+    Ctx c{h, N, N, keep_L, info_dev, 1, (int64_t)N * N, 0};
+    double* Tdiag = T;
+    double* Trow = T + rec_scratch_doubles(nbk);
+    cudaStream_t M = h->stream, S = h->pipe[0], S2 = h->pipe[1];
+    cudaEvent_t ev = next_event(h);
+    GPK_CUDA(h, cudaEventRecord(ev, M));            // K is built (and earlier users of the buffers are done) before S/S2 start
+    GPK_CUDA(h, cudaStreamWaitEvent(S, ev, 0));
+    GPK_CUDA(h, cudaStreamWaitEvent(S2, ev, 0));
+    cudaEvent_t evGcol_prev = nullptr;              // S finished block column k+1 of trailing update k-1
+    int rc;
+    for (int k = 0; k < nt; ++k) {
+        const int bk = bs(k), sk = bs(k + 1) - bk;
+        rc = potrf_inv_rec(c, A + bk + (int64_t)bk * N, Li + bk + (int64_t)bk * N, Tdiag, sk, bk, 0);              // F_k
+        if (rc) return rc;
+        cudaEvent_t evF = next_event(h);
+        GPK_CUDA(h, cudaEventRecord(evF, M));
+        if (k + 1 < nt) {
+            const int b1 = bs(k + 1), s1 = bs(k + 2) - b1;
+            GemmDesc g = gemm_desc();                                                                                // P_k
+            g.P = Li + bk + (int64_t)bk * N; g.ldp = N; g.p_kcontig = 0;
+            g.Q = A + b1 + (int64_t)bk * N; g.ldq = N; g.q_kcontig = 0;
+            g.D = Li + b1 + (int64_t)bk * N; g.ldd = N;
+            g.R = sk; g.S = N - b1; g.K = sk; g.ke_r = 1; g.heavy_last = 1;
+            rc = gpk_gemm(h, g);
+            if (rc) return rc;
+            if (keep_L) {
+                rc = gpk_copy2d(h, A + b1 + (int64_t)bk * N, N, Li + b1 + (int64_t)bk * N, N, N - b1, sk);
+                if (rc) return rc;
+            }
+            cudaEvent_t evE = next_event(h);
+            GPK_CUDA(h, cudaEventRecord(evE, M));
+            if (evGcol_prev) GPK_CUDA(h, cudaStreamWaitEvent(M, evGcol_prev, 0));
+            rc = col_update(h, A, Li, N, bk, sk, b1, s1);                                                            // U_k(:,k+1)
+            if (rc) return rc;
+            evGcol_prev = nullptr;
+            if (k + 2 < nt) {
+                GPK_CUDA(h, cudaStreamWaitEvent(S, evE, 0));
+                StreamSwap sw(h, S);
+                const int b2 = bs(k + 2), s2 = bs(k + 3) - b2;
+                rc = col_update(h, A, Li, N, bk, sk, b2, s2);                                                        // U_k(:,k+2)
+                if (rc) return rc;
+                evGcol_prev = next_event(h);
+                GPK_CUDA(h, cudaEventRecord(evGcol_prev, S));
+                if (k + 3 < nt) {
+                    const int b3 = bs(k + 3);
+                    rc = col_update(h, A, Li, N, bk, sk, b3, N - b3);                                                // U_k(k+3:, k+3:)
+                    if (rc) return rc;
+                }
+            }
+        }
+        GPK_CUDA(h, cudaStreamWaitEvent(S2, evF, 0));
+        StreamSwap sw(h, S2);
+        const double* Likk = Li + bk + (int64_t)bk * N;
+        if (k > 0) {
+            rc = gemm_T(c, Li + bk, N, 0, Li, Trow, bk, sk);                      // T_k = L_{k,0:k} Li_{0:k,0:k}   (sk x bk, ld sk)
+            if (rc) return rc;
+            rc = gemm_Li21(c, Trow, Likk, Li + bk, bk, sk);                       // Li_{k,0:k} = -Li_kk T_k
+            if (rc) return rc;
+        }
+        if (Kinv) {
+            GemmDesc g;
+            if (k > 0) {
+                g = gemm_desc();                                                  // Kinv[k,0:k] = Li_kk^t Li_{k,0:k}
+                g.P = Li + bk; g.ldp = N; g.p_kcontig = 1;                        // P(r,q) = Li(bk+q, r)
+                g.Q = Likk; g.ldq = N; g.q_kcontig = 1;                           // Q(s,q) = Li_kk(q, s), zero for q < s
+                g.D = Kinv + bk; g.ldd = N; g.R = bk; g.S = sk; g.K = sk; g.kb_s = 1;
+                rc = gpk_gemm(h, g);
+                if (rc) return rc;
+            }
+            g = gemm_desc();                                                      // Kinv[k,k] = Li_kk^t Li_kk (lower)
+            g.P = Likk; g.ldp = N; g.p_kcontig = 1;
+            g.Q = Likk; g.ldq = N; g.q_kcontig = 1;
+            g.D = Kinv + bk + (int64_t)bk * N; g.ldd = N; g.R = sk; g.S = sk; g.K = sk; g.kb_r = 1; g.kb_s = 1; g.tri_out = 1;
+            rc = gpk_gemm(h, g);
+            if (rc) return rc;
+            if (k > 0) {
+                g = gemm_desc();                                                  // Kinv[0:k,0:k] += Li_{k,0:k}^t Li_{k,0:k} (lower)
+                g.P = Li + bk; g.ldp = N; g.p_kcontig = 1;
+                g.Q = Li + bk; g.ldq = N; g.q_kcontig = 1;
+                g.D = Kinv; g.ldd = N; g.Cin = Kinv; g.ldc = N; g.R = bk; g.S = bk; g.K = sk; g.beta = 1.0; g.tri_out = 1;
+                rc = gpk_gemm(h, g);
+                if (rc) return rc;
+            }
+        }
+    }
+    cudaEvent_t e1 = next_event(h), e2 = next_event(h);
+    GPK_CUDA(h, cudaEventRecord(e1, S));
+    GPK_CUDA(h, cudaEventRecord(e2, S2));
+    GPK_CUDA(h, cudaStreamWaitEvent(M, e1, 0));
+    GPK_CUDA(h, cudaStreamWaitEvent(M, e2, 0));
+    return GPK_OK;
+}
+
+bool gpk_use_pipelined(int N, int batch) { return batch == 1 && pipe_min() > 0 && N >= pipe_min() && N >= 2 * pipe_nb(); }
+
 int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int* info_dev, int batch) {
+    if (gpk_use_pipelined(N, batch)) return gpk_potrf_inv_pipelined(h, A, Li, nullptr, T, N, keep_L, info_dev);
     GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int) * (size_t)batch, h->stream));
     Ctx c{h, N, N, keep_L, info_dev, batch, (int64_t)N * N, (int64_t)gpk_chol_scratch_doubles(N)};
     return potrf_inv_rec(c, A, Li, T, N, 0, 0);

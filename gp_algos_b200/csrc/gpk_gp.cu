@@ -89,11 +89,14 @@ int stage_params(gpk_handle h, const double* thetas, int D, int has_s, double s,
 
 // K -> L^-1 (and L when keep_L), alpha, ll for `B` resident problems.  X, y on the device.
 int fit_core(gpk_handle h, const Work& w, int B, const double* dX, int n, int D, int64_t ldx, int64_t strideX, const double* dy,
-             const ProblemParams& pp0, int keep_L, double* Li, double* alpha, double* ll_dev, int64_t ll_stride, int* info_dev) {
+             const ProblemParams& pp0, int keep_L, double* Li, double* alpha, double* ll_dev, int64_t ll_stride, int* info_dev,
+             double* Kinv = nullptr) {
     const ProblemParams* ppd = (B > 1) ? w.pp_dev : nullptr;
     int rc = gpk_cov_sym_lower_padded(h, dX, n, ldx, pp0.cp, w.A, w.N, B, strideX, ppd);
     if (rc) return rc;
-    rc = gpk_potrf_inv(h, w.A, Li, w.T, w.N, keep_L, info_dev, B);
+    // Kinv != nullptr: the look-ahead driver also accumulates K^-1 = L^-t L^-1 while it factors (one large problem only)
+    rc = Kinv ? gpk_potrf_inv_pipelined(h, w.A, Li, Kinv, w.T, w.N, keep_L, info_dev)
+              : gpk_potrf_inv(h, w.A, Li, w.T, w.N, keep_L, info_dev, B);
     if (rc) return rc;
     rc = gpk_pad_vector(h, w.ypad, w.N, dy, n, B);
     if (rc) return rc;
@@ -117,12 +120,19 @@ int nll_grad_core(gpk_handle h, int B, const double* dX, int n, int D, int64_t l
         if (rc) return rc;
         const double* X = dX + b0 * strideX;
         int* info = info_dev ? info_dev + b0 : (B == 1 ? h->d_info : w.info_dev);
-        rc = fit_core(h, w, bc, X, n, D, ldx, strideX, dy + (size_t)b0 * n, pp0, 0, w.Li, w.alpha, out_dev + b0 * so, so, info);
+        double* Kinv = nullptr;
+        if (nparams > 0 && gpk_use_pipelined(w.N, bc)) {
+            Kinv = (double*)gpk_arena(h, ARENA_KINV, (size_t)w.N * w.N * sizeof(double));
+            if (!Kinv) return GPK_ENOMEM;
+        }
+        rc = fit_core(h, w, bc, X, n, D, ldx, strideX, dy + (size_t)b0 * n, pp0, 0, w.Li, w.alpha, out_dev + b0 * so, so, info, Kinv);
         if (rc) return rc;
         if (nparams > 0) {
-            rc = gpk_lauum_lower(h, w.Li, w.A, w.N, bc);  // K^-1 = L^-t L^-1 (GpPredictor.scala:67), lower tiles, into A
-            if (rc) return rc;
-            rc = gpk_grad_trace(h, w.A, w.N, X, n, ldx, w.alpha, pp0, nparams, out_dev + b0 * so + 1, w.scratch, bc, strideX,
+            if (!Kinv) {
+                rc = gpk_lauum_lower(h, w.Li, w.A, w.N, bc);  // K^-1 = L^-t L^-1 (GpPredictor.scala:67), lower tiles, into A
+                if (rc) return rc;
+            }
+            rc = gpk_grad_trace(h, Kinv ? Kinv : w.A, w.N, X, n, ldx, w.alpha, pp0, nparams, out_dev + b0 * so + 1, w.scratch, bc, strideX,
                                 bc > 1 ? w.pp_dev : nullptr, so);
             if (rc) return rc;
         }

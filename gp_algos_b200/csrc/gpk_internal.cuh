@@ -16,6 +16,7 @@ struct gpk_handle_s {
     cudaStream_t stream;
     bool own_stream;
     cudaStream_t side[GPK_NSIDE];
+    cudaStream_t pipe[2];    // lowest-priority streams of the pipelined factorisation (trailing updates; inverse rows + K^-1)
     cudaEvent_t evpool[GPK_NEVENTS];
     unsigned ev_next;
     // grow-only device arenas (A: factor / K^-1, B: L^-1, T: GEMM scratch, misc: small vectors)
@@ -31,7 +32,7 @@ struct gpk_handle_s {
     char err[512];
 };
 
-enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7, ARENA_PP = 8, ARENA_INFO = 9, ARENA_GEMV = 10, GPK_NARENA = 12 };
+enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7, ARENA_PP = 8, ARENA_INFO = 9, ARENA_GEMV = 10, ARENA_KINV = 11, GPK_NARENA = 12 };
 
 int gpk_set_error(gpk_handle h, int status, const char* fmt, ...);
 // returns device pointer to at least `bytes` bytes in arena `which` (contents undefined after growth)
@@ -141,6 +142,10 @@ int gpk_base_potrf_trtri(gpk_handle h, double* A, int64_t lda, double* Li, int64
                          int batch, int64_t strideA, int64_t strideLi, int info_stride, int coloff_stride);
 size_t gpk_chol_scratch_doubles(int N);
 int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int* info_dev, int batch = 1);
+// Look-ahead driver for one large problem (see gpk_chol.cu): same results as gpk_potrf_inv; when Kinv != nullptr it also
+// accumulates K^-1 = Li^t Li (lower tiles) into Kinv (N x N, ld N, a buffer distinct from A and Li).
+bool gpk_use_pipelined(int N, int batch);
+int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev);
 // L^-1 for a given lower-triangular L (N x N padded, ld N)
 int gpk_trtri_lower(gpk_handle h, const double* L, double* Li, double* T, int N);
 // Kinv (lower triangle incl. diagonal tiles in full) = Li^t Li

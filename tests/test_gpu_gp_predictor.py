@@ -143,7 +143,7 @@ def test_requirements_and_errors():
 
 
 # ---- LAPACK-backed oracle at larger sizes and the BASELINE.json size --------------------------------------------
-@pytest.mark.parametrize("n", [1024, 2500, 4096])
+@pytest.mark.parametrize("n", [1024, 2500, 4096, 4500, 6000])   # >= 3969 pads to N >= 4096: the look-ahead (pipelined) driver
 def test_loglik_gradient_vs_fast_oracle(n):
     X, y, th = orc.make_c2(n=n, D=8)
     ll, g = _pred(th).logLikelihoodWithDerivatives(gp.PredictionTrainingInput(X, None, y), th, 10)

@@ -82,7 +82,7 @@ def test_cov_deriv_matrices():
 
 
 # ---- cholesky ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 255, 384, 640, 1000, 1500])
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 255, 384, 640, 1000, 1500, 4300])   # 4300 -> N = 4352: pipelined driver with keep_L
 def test_cholesky_backward_error_and_parity(n):
     import scipy.linalg as sla
     X, y, th = orc.make_c2(n=n, D=8, seed=n)
