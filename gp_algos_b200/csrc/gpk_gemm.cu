@@ -120,29 +120,47 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_BLOCKS) gemm_f64_dmma_kernel
 #pragma unroll
         for (int j = 0; j < BJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // Per-thread copy descriptors: running global pointers (advanced by one k-chunk per issue) and fixed offsets inside a
+    // stage, so the steady-state loop carries no 64-bit address arithmetic and no `% STAGES`.
+    constexpr int PPT = TR * TK / 2 / NT, QPT = TS * TK / 2 / NT;
+    const double* pg[PPT];
+    const double* qg[QPT];
+    int pso[PPT], qso[QPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int c = tid + i * NT;
+        if (!PK) { const int k = c / (TR / 2), x = (c % (TR / 2)) * 2; pso[i] = k * LDRP + x; pg[i] = P + (int64_t)(kbeg + k) * g.ldp + (r0 + x); }
+        else     { const int x = c >> 3, k = (c & 7) * 2;              pso[i] = x * LDK + k;  pg[i] = P + (int64_t)(r0 + x) * g.ldp + (kbeg + k); }
+    }
+#pragma unroll
+    for (int i = 0; i < QPT; ++i) {
+        const int c = tid + i * NT;
+        if (!QK) { const int k = c / (TS / 2), x = (c % (TS / 2)) * 2; qso[i] = k * LDRQ + x; qg[i] = Q + (int64_t)(kbeg + k) * g.ldq + (s0 + x); }
+        else     { const int x = c >> 3, k = (c & 7) * 2;              qso[i] = x * LDK + k;  qg[i] = Q + (int64_t)(s0 + x) * g.ldq + (kbeg + k); }
+    }
+    const int64_t pstep = PK ? (int64_t)TK : (int64_t)TK * g.ldp;
+    const int64_t qstep = QK ? (int64_t)TK : (int64_t)TK * g.ldq;
+    auto issue = [&](int stage) {
+        double* pst = Ps + stage * Cfg::P_STAGE;
+        double* qst = Qs + stage * Cfg::Q_STAGE;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) { cp_async16(pst + pso[i], pg[i]); pg[i] += pstep; }
+#pragma unroll
+        for (int i = 0; i < QPT; ++i) { cp_async16(qst + qso[i], qg[i]); qg[i] += qstep; }
+    };
+
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) {
-            load_tile<PK, TR, NT>(Ps + s * Cfg::P_STAGE, P, g.ldp, r0, kbeg + s * TK, tid);
-            load_tile<QK, TS, NT>(Qs + s * Cfg::Q_STAGE, Q, g.ldq, s0, kbeg + s * TK, tid);
-        }
+        if (s < nk) issue(s);
         cp_async_commit();
     }
 
+    int cstage = 0, lstage = STAGES - 1;   // stage computed on / stage loaded into, both cycle through 0..STAGES-1
     for (int kc = 0; kc < nk; ++kc) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            const int nx = kc + STAGES - 1;
-            if (nx < nk) {
-                const int st = nx % STAGES;
-                load_tile<PK, TR, NT>(Ps + st * Cfg::P_STAGE, P, g.ldp, r0, kbeg + nx * TK, tid);
-                load_tile<QK, TS, NT>(Qs + st * Cfg::Q_STAGE, Q, g.ldq, s0, kbeg + nx * TK, tid);
-            }
-            cp_async_commit();
-        }
-        const double* ps = Ps + (kc % STAGES) * Cfg::P_STAGE;
-        const double* qs = Qs + (kc % STAGES) * Cfg::Q_STAGE;
+        const double* ps = Ps + cstage * Cfg::P_STAGE;
+        const double* qs = Qs + cstage * Cfg::Q_STAGE;
         const double* pf = PK ? ps + (wr0 + gid) * LDK + tig : ps + tig * LDRP + wr0 + gid;
         const double* qf = QK ? qs + (ws0 + gid) * LDK + tig : qs + tig * LDRQ + ws0 + gid;
 #pragma unroll
@@ -156,7 +174,15 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_BLOCKS) gemm_f64_dmma_kernel
             for (int i = 0; i < BI; ++i)
 #pragma unroll
                 for (int j = 0; j < BJ; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+            if (kk == 0) {
+                // refill the stage that was consumed in the previous iteration (every warp is past the barrier above, so
+                // nobody reads it any more); issued behind the first DMMA group so the copies overlap the math
+                if (kc + STAGES - 1 < nk) issue(lstage);
+                cp_async_commit();
+            }
         }
+        cstage = (cstage + 1 == STAGES) ? 0 : cstage + 1;
+        lstage = (lstage + 1 == STAGES) ? 0 : lstage + 1;
     }
     cp_async_wait<0>();
 
