@@ -123,6 +123,37 @@ class GpPredictor:
                                      int(s is not None), float(s or 0.0), _lib.ptr(mean), _lib.ptr(sigma), m, C.addressof(ll)))
         return GaussianDistribution(mean, sigma), ll.value
 
+    # ---- GpPredictor.scala:126-142 ---------------------------------------------------------------------
+    def obtainOptimalHyperParams(self, trainingData, sigmaNoise, targets, optimizeNoise: bool, optimizer=None):
+        """L-BFGS(m = 4, maxIter = 20) maximisation of logLikelihoodWithDerivatives in the natural parameters; returns the
+        best point seen (optimization/Optimization.scala:37-61).  The optimiser is host control flow (Breeze's in the
+        reference, `BreezeLbfgsOptimizer` here); every objective/gradient evaluation is one gpk_gp_nll_grad call.
+        optimizeNoise = False reproduces the reference's defect: the start point drops the noise entry
+        (`toDenseVector(0 to -2)`, :130-132) and `fromDenseVector` then fails its length `require`
+        (KernelRequisites.scala:55) on the first evaluation."""
+        from .gp_optimizer import BreezeLbfgsOptimizer
+        opt = optimizer or BreezeLbfgsOptimizer(maxIter=20)
+        hp = self.kernelFunc.hyperParams
+        init = hp.toDenseVector if optimizeNoise else hp.toDenseVector[:-1]
+        ptInput = PredictionTrainingInput(trainingData, sigmaNoise, targets)
+
+        def llObjFunction(currentParams):
+            hyperParams = hp.fromDenseVector(np.asarray(currentParams, dtype=np.float64))
+            return self.logLikelihoodWithDerivatives(ptInput, hyperParams, len(currentParams))
+
+        return hp.fromDenseVector(opt.maximize(llObjFunction, np.asarray(init, dtype=np.float64)))
+
+    # ---- GpPredictor.scala:82-87 -----------------------------------------------------------------------
+    def predictWithParamsOptimization(self, input: PredictionInput, optimizeNoise: bool, optimizer=None):
+        optimal = self.obtainOptimalHyperParams(input.trainingData, input.sigmaNoise, input.targets, optimizeNoise, optimizer)
+        dist, ll = self.predict(input, optimal)
+        return dist, ll, optimal
+
+    # ---- GpPredictor.scala:96-101 ----------------------------------------------------------------------
+    def preComputeComponentsWithHpOptimization(self, trainingData, sigmaNoise, targets, optimizer=None):
+        optimal = self.obtainOptimalHyperParams(trainingData, sigmaNoise, targets, True, optimizer)
+        return self.preComputeComponents(trainingData, sigmaNoise, targets, optimal), optimal
+
     # ---- GpPredictor.scala:45-58 ----------------------------------------------------------------------
     def computePosterior(self, trainingData, testData, l, alphaVec, kernelFunc=None):
         """-> (GaussianDistribution(mean, sigma), vMatrix).  The factor `l` is adopted on the device

@@ -104,3 +104,31 @@ def test_scalar_kernel_matches_oracle():
         assert abs(f(X[1], X[2], False) - dK[1, 2]) <= 1e-14 * max(abs(dK[1, 2]), 1e-300)
     with pytest.raises(LookupError):
         kf.derAfterHyperParam(6)
+
+
+def test_breeze_lbfgs_wrapper_best_seen_logic():   # optimization/Optimization.scala:37-61
+    from gp_algos_b200.gp_optimizer import BreezeLbfgsOptimizer
+    calls = []
+
+    def f(p):   # concave quadratic with maximum at (1, -2)
+        calls.append(np.array(p))
+        return -((p[0] - 1.0) ** 2 + 2.0 * (p[1] + 2.0) ** 2), np.array([-2.0 * (p[0] - 1.0), -4.0 * (p[1] + 2.0)])
+
+    x = BreezeLbfgsOptimizer(20).maximize(f, [5.0, 5.0])
+    assert np.allclose(x, [1.0, -2.0], atol=1e-6)
+    assert len(calls) >= 3                                # objective evaluated through the minus-wrapper, plus the final re-evaluation
+    xm = BreezeLbfgsOptimizer(20).minimize(lambda p: (float(np.sum((np.asarray(p) - 3.0) ** 2)), 2.0 * (np.asarray(p) - 3.0)), [0.0, 0.0, 0.0])
+    assert np.allclose(xm, 3.0, atol=1e-6)
+    # maxIter = 0-like behaviour: with one iteration the best-seen point is still returned, never something worse than the start
+    x1 = BreezeLbfgsOptimizer(1).maximize(f, [5.0, 5.0])
+    assert f(x1)[0] >= f([5.0, 5.0])[0]
+
+
+def test_obtain_optimal_hyper_params_without_noise_throws_like_the_reference():
+    """GpPredictor.scala:130-132 drops the noise entry from the start point and KernelRequisites.scala:55 then rejects the
+    shorter vector: `optimizeNoise = false` always throws in the reference; no GPU is reached."""
+    import gp_algos_b200 as gp
+    pred = gp.GpPredictor(gp.GaussianRbfKernel(gp.GaussianRbfParams(1.0, [1.0, 2.0], 0.1)))
+    X = np.random.default_rng(0).uniform(size=(10, 2)); y = X[:, 0]
+    with pytest.raises(ValueError, match="does not equal to 4"):
+        pred.obtainOptimalHyperParams(X, None, y, optimizeNoise=False)

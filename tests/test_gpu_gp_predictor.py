@@ -190,3 +190,21 @@ def test_boston_soft_fixture_ill_conditioned():
     assert np.abs(dist.mean - g["oracle_mean"]).max() <= 1e-6 * np.abs(g["oracle_mean"]).max()
     assert np.abs(np.sqrt(np.diag(dist.sigma)) - g["oracle_std"]).max() <= 1e-6
     assert np.abs(dist.mean[:nt] - g["ref_mean"][:nt]).max() <= 2e-3 * np.abs(g["ref_mean"][:nt]).max()
+
+
+def test_obtain_optimal_hyper_params_improves_the_likelihood():   # GpPredictor.scala:126-142 + Optimization.scala:30-61
+    X, y, th = orc.make_c2(n=400, D=3, seed=12)
+    start = orc.pack_theta(0.7, [1.5, 1.5, 1.5], 0.3)
+    p = _pred(start)
+    inp = gp.PredictionTrainingInput(X, None, y)
+    ll0, _ = p.logLikelihoodWithDerivatives(inp, start, 5)
+    best = p.obtainOptimalHyperParams(X, None, y, optimizeNoise=True)
+    ll1, g1 = p.logLikelihoodWithDerivatives(inp, best, 5)
+    assert ll1 > ll0 + 10.0
+    # the same optimiser over the oracle's objective lands on the same optimum (objective/gradient agree to 1e-9 per call)
+    from gp_algos_b200 import BreezeLbfgsOptimizer
+    xo = BreezeLbfgsOptimizer(20).maximize(lambda t: orc.fast_loglik_with_derivs(X, y, np.asarray(t)), start)
+    llo, _ = orc.fast_loglik_with_derivs(X, y, xo)
+    assert abs(ll1 - llo) <= 1e-6 * abs(llo)
+    dist, ll, hp = p.predictWithParamsOptimization(gp.PredictionInput(X, X[:5], None, y), True)
+    assert abs(ll - ll1) <= 1e-9 * abs(ll1) and hp == best and dist.mean.shape == (5,)
