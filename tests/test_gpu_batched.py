@@ -92,3 +92,20 @@ def test_c4_shape_subset_full_n():
         mo, vo, _ = orc.fast_compute_posterior(X[b], Xs[b], Lo, ao, th[b], full_cov=False)
         assert np.all(np.abs(mean[b] - mo) <= RTOL * np.abs(mo).max())
         assert np.all(np.abs(var[b] - vo) <= RTOL * np.abs(vo))
+
+
+def test_c4_config_full_size_sampled_parity_and_partition_invariance():
+    """BASELINE.json config 4 at full size (512 problems of n = 1024, D = 8): three sampled problems against the LAPACK-backed
+    oracle, every problem finite, and the size-independent property that any partition of the batch gives identical results."""
+    B = 512
+    probs = [orc.make_c4_problem(b) for b in range(B)]
+    X = np.stack([p[0] for p in probs]); ys = np.stack([p[1] for p in probs]); th = np.stack([p[3] for p in probs])
+    ll, grad, info = batched.log_likelihood_with_derivatives_batched(X, ys, th)
+    assert np.all(info == 0) and np.all(np.isfinite(ll)) and np.all(np.isfinite(grad))
+    for b in (0, 255, 511):
+        llo, go = orc.fast_loglik_with_derivs(X[b], ys[b], th[b])
+        assert abs(ll[b] - llo) <= RTOL * abs(llo)
+        assert _grad_ok(grad[b], go)
+    lo, hi = batched.shard_bounds(B, 5, 8)                                   # the shard rank 5 of 8 would evaluate
+    ll_s, grad_s, _ = batched.log_likelihood_with_derivatives_batched(X[lo:hi], ys[lo:hi], th[lo:hi])
+    assert np.array_equal(ll_s, ll[lo:hi]) and np.array_equal(grad_s, grad[lo:hi])

@@ -64,3 +64,24 @@ def test_two_gpus_nccl_matches_single_gpu():
         assert outs[grid]["residual_Kalpha_minus_y_over_y"] < 1e-10
     for grid in ("2x1", "1x2"):
         assert abs(outs[grid]["ll"] - outs["1x1"]["ll"]) <= 1e-11 * abs(outs["1x1"]["ll"])
+
+
+def test_single_gpu_medium_size_residual_and_loglik_against_resident_model():
+    """n = 12288 (12 block columns of 1024): the block-cyclic solver and the single-handle path (gpk_gp_model_fit) must
+    agree on alpha and the log-likelihood, and K alpha = y must hold -- no oracle needed at this size."""
+    import gp_algos_b200 as gp
+    from gp_algos_b200.distributed import DistributedGp
+    X, y, theta = orc_make(12288)
+    solver = DistributedGp(nb=1024, device=0)
+    fit = solver.fit(X, y, theta)
+    assert solver.residual(y, fit.alphaVec) < 1e-10
+    pred = gp.GpPredictor(gp.GaussianRbfKernel(gp.GaussianRbfParams(theta[0], theta[1:-1], theta[-1])))
+    model = pred.fit(X, None, y, theta)
+    assert abs(model.logLikelihood - fit.logLikelihood) <= 1e-11 * abs(fit.logLikelihood)
+    assert np.allclose(model.alphaVec, fit.alphaVec, rtol=1e-7, atol=1e-9 * np.abs(fit.alphaVec).max())
+    model.close()
+
+
+def orc_make(n):
+    from oracle import gp_oracle as orc
+    return orc.make_c2(n=n, D=8, seed=5)

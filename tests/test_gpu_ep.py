@@ -121,3 +121,28 @@ def test_ep_requirements():
         gp.EpParameterEstimator(np.eye(4), np.ones(3, dtype=np.int32), gp.FixedSweeps(1))
     with pytest.raises(TypeError):
         gp.EpParameterEstimator(np.eye(4), np.ones(4, dtype=np.int32), lambda ctx: True).estimateSiteParams
+
+
+def test_c3_config_full_size_properties():
+    """BASELINE.json config 3 at full size (n = 4096, D = 4): the CPU oracle needs minutes per sweep here, so the check is
+    through size-independent properties of a finished EP run."""
+    X, t, th = orc.make_c3()
+    n = X.shape[0]
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
+    K = gp.MatrixUtils.buildKernelMatrix(kf, X)
+    est = gp.EpParameterEstimator(K, t, gp.FixedSweeps(3))
+    site, L = est.estimateSiteParams
+    tau, nu = site.tauSiteParams, site.niSiteParams
+    assert est.sweeps == 3 and np.all(np.isfinite(tau)) and np.all(tau > 0) and np.all(np.isfinite(nu))
+    st = np.sqrt(tau)
+    Bm = np.eye(n) + (st[:, None] * st[None, :]) * K                          # EpParameterEstimator.scala:58
+    assert np.linalg.norm(L @ L.T - Bm) <= 8 * n * np.finfo(float).eps * np.linalg.norm(Bm)
+    assert np.all(np.triu(L, 1) == 0.0)
+    # mu = Sigma nu with Sigma = (K^-1 + S)^-1 = K - K S^1/2 B^-1 S^1/2 K  (:60-61): check (K^-1 + S) mu = nu  <=>  mu + K S mu = K nu
+    mu = est.mu
+    assert np.linalg.norm(mu + K @ (tau * mu) - K @ nu) <= 1e-8 * np.linalg.norm(K @ nu)
+    # a second, identical run is bit-identical (deterministic reductions, fixed stream order)
+    site2, _ = gp.EpParameterEstimator(K, t, gp.FixedSweeps(3)).estimateSiteParams
+    assert np.array_equal(site2.tauSiteParams, tau) and site2.marginalLogLikelihood == site.marginalLogLikelihood
+    p = gp.GpClassifier(gp.FixedSweeps(3)).classify(gp.AfterEstimationClassifierInput(t, (site, L), None, K, K[:64], K[:64, :64]))
+    assert np.all((p > 0) & (p < 1)) and np.mean((p > 0.5) == (t[:64] > 0)) > 0.85
