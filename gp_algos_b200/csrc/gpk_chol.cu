@@ -50,7 +50,7 @@ int side_min() {
 
 int pipe_nb() {      // block-column width of the pipelined driver
     static int v = -1;
-    if (v < 0) { const char* e = getenv("GPK_PIPE_NB"); v = e ? atoi(e) : 1024; if (v < NB || v % NB) v = 1024; }
+    if (v < 0) { const char* e = getenv("GPK_PIPE_NB"); v = e ? atoi(e) : 512; if (v < NB || v % NB) v = 512; }   // measured at n = 8192: 384 20.4, 512 19.1, 640 19.5, 768 19.7, 1024 19.3 ms
     return v;
 }
 int pipe_min() {     // smallest padded N that takes the pipelined driver (0 disables it)
@@ -209,7 +209,8 @@ int col_update(gpk_handle h, double* A, const double* Li, int N, int bk, int sk,
 
 }  // namespace
 
-int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev) {
+int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev,
+                            cudaEvent_t* kinv_done) {
     const int nbk = pipe_nb();
     const int nt = (N + nbk - 1) / nbk;
     auto bs = [&](int k) { return k * nbk < N ? k * nbk : N; };
@@ -223,6 +224,7 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     GPK_CUDA(h, cudaStreamWaitEvent(S, ev, 0));
     GPK_CUDA(h, cudaStreamWaitEvent(S2, ev, 0));
     cudaEvent_t evGcol_prev = nullptr;              // S finished block column k+1 of trailing update k-1
+    cudaEvent_t evLi = nullptr;                     // S2 finished the last row of L^-1
     int rc;
     for (int k = 0; k < nt; ++k) {
         const int bk = bs(k), sk = bs(k + 1) - bk;
@@ -273,6 +275,10 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
             rc = gemm_Li21(c, Trow, Likk, Li + bk, bk, sk);                       // Li_{k,0:k} = -Li_kk T_k
             if (rc) return rc;
         }
+        if (k == nt - 1) {                                                        // L^-1 is complete
+            evLi = next_event(h);
+            GPK_CUDA(h, cudaEventRecord(evLi, S2));
+        }
         if (Kinv) {
             GemmDesc g;
             if (k > 0) {
@@ -299,18 +305,27 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
             }
         }
     }
+    // join: the caller's stream continues once L and L^-1 are complete.  With kinv_done != nullptr the K^-1 accumulation of
+    // the last row (the largest) keeps running on S2 and the caller waits for *kinv_done only where it reads K^-1, so
+    // alpha = L^-t L^-1 y and the log-likelihood overlap it.
     cudaEvent_t e1 = next_event(h), e2 = next_event(h);
     GPK_CUDA(h, cudaEventRecord(e1, S));
     GPK_CUDA(h, cudaEventRecord(e2, S2));
     GPK_CUDA(h, cudaStreamWaitEvent(M, e1, 0));
-    GPK_CUDA(h, cudaStreamWaitEvent(M, e2, 0));
+    if (kinv_done && Kinv && evLi) {
+        GPK_CUDA(h, cudaStreamWaitEvent(M, evLi, 0));
+        *kinv_done = e2;
+    } else {
+        GPK_CUDA(h, cudaStreamWaitEvent(M, e2, 0));
+        if (kinv_done) *kinv_done = nullptr;
+    }
     return GPK_OK;
 }
 
 bool gpk_use_pipelined(int N, int batch) { return batch == 1 && pipe_min() > 0 && N >= pipe_min() && N >= 2 * pipe_nb(); }
 
 int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int* info_dev, int batch) {
-    if (gpk_use_pipelined(N, batch)) return gpk_potrf_inv_pipelined(h, A, Li, nullptr, T, N, keep_L, info_dev);
+    if (gpk_use_pipelined(N, batch)) return gpk_potrf_inv_pipelined(h, A, Li, nullptr, T, N, keep_L, info_dev, nullptr);
     GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int) * (size_t)batch, h->stream));
     Ctx c{h, N, N, keep_L, info_dev, batch, (int64_t)N * N, (int64_t)gpk_chol_scratch_doubles(N)};
     return potrf_inv_rec(c, A, Li, T, N, 0, 0);

@@ -37,7 +37,7 @@ struct Work {
 
 size_t per_problem_doubles(int N, int D, size_t* sT, size_t* sScr) {
     *sT = gpk_chol_scratch_doubles(N);
-    const size_t trmv = (size_t)(N / 1024 + 1) * N;
+    const size_t trmv = gpk_trmv_scratch_doubles(N);
     const size_t grad = gpk_grad_scratch_doubles(N, D);
     *sScr = trmv > grad ? trmv : grad;
     return (size_t)2 * N * N + *sT + (size_t)3 * N + *sScr;
@@ -90,12 +90,12 @@ int stage_params(gpk_handle h, const double* thetas, int D, int has_s, double s,
 // K -> L^-1 (and L when keep_L), alpha, ll for `B` resident problems.  X, y on the device.
 int fit_core(gpk_handle h, const Work& w, int B, const double* dX, int n, int D, int64_t ldx, int64_t strideX, const double* dy,
              const ProblemParams& pp0, int keep_L, double* Li, double* alpha, double* ll_dev, int64_t ll_stride, int* info_dev,
-             double* Kinv = nullptr) {
+             double* Kinv = nullptr, cudaEvent_t* kinv_done = nullptr) {
     const ProblemParams* ppd = (B > 1) ? w.pp_dev : nullptr;
     int rc = gpk_cov_sym_lower_padded(h, dX, n, ldx, pp0.cp, w.A, w.N, B, strideX, ppd);
     if (rc) return rc;
     // Kinv != nullptr: the look-ahead driver also accumulates K^-1 = L^-t L^-1 while it factors (one large problem only)
-    rc = Kinv ? gpk_potrf_inv_pipelined(h, w.A, Li, Kinv, w.T, w.N, keep_L, info_dev)
+    rc = Kinv ? gpk_potrf_inv_pipelined(h, w.A, Li, Kinv, w.T, w.N, keep_L, info_dev, kinv_done)
               : gpk_potrf_inv(h, w.A, Li, w.T, w.N, keep_L, info_dev, B);
     if (rc) return rc;
     rc = gpk_pad_vector(h, w.ypad, w.N, dy, n, B);
@@ -125,8 +125,11 @@ int nll_grad_core(gpk_handle h, int B, const double* dX, int n, int D, int64_t l
             Kinv = (double*)gpk_arena(h, ARENA_KINV, (size_t)w.N * w.N * sizeof(double));
             if (!Kinv) return GPK_ENOMEM;
         }
-        rc = fit_core(h, w, bc, X, n, D, ldx, strideX, dy + (size_t)b0 * n, pp0, 0, w.Li, w.alpha, out_dev + b0 * so, so, info, Kinv);
+        cudaEvent_t kinv_done = nullptr;
+        rc = fit_core(h, w, bc, X, n, D, ldx, strideX, dy + (size_t)b0 * n, pp0, 0, w.Li, w.alpha, out_dev + b0 * so, so, info, Kinv,
+                      &kinv_done);
         if (rc) return rc;
+        if (kinv_done) GPK_CUDA(h, cudaStreamWaitEvent(h->stream, kinv_done, 0));   // alpha / ll above overlapped the last K^-1 row
         if (nparams > 0) {
             if (!Kinv) {
                 rc = gpk_lauum_lower(h, w.Li, w.A, w.N, bc);  // K^-1 = L^-t L^-1 (GpPredictor.scala:67), lower tiles, into A

@@ -145,7 +145,10 @@ int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int kee
 // Look-ahead driver for one large problem (see gpk_chol.cu): same results as gpk_potrf_inv; when Kinv != nullptr it also
 // accumulates K^-1 = Li^t Li (lower tiles) into Kinv (N x N, ld N, a buffer distinct from A and Li).
 bool gpk_use_pipelined(int N, int batch);
-int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev);
+// kinv_done != nullptr: returns without waiting for the K^-1 accumulation; the caller must cudaStreamWaitEvent(*kinv_done)
+// (when non-null) on its stream before reading Kinv.
+int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev,
+                            cudaEvent_t* kinv_done = nullptr);
 // L^-1 for a given lower-triangular L (N x N padded, ld N)
 int gpk_trtri_lower(gpk_handle h, const double* L, double* Li, double* T, int N);
 // Kinv (lower triangle incl. diagonal tiles in full) = Li^t Li
@@ -154,7 +157,8 @@ int gpk_lauum_lower(gpk_handle h, const double* Li, double* Kinv, int N, int bat
 // ---------------------------------------------------------------------------------------------
 // vectors / reductions / gradient (gpk_vec.cu, gpk_grad.cu)
 // ---------------------------------------------------------------------------------------------
-// z = Li * y (lower-triangular matvec, N padded; y has N entries with zeros in the padding); scratch: (N/1024+1)*N per problem
+// z = Li * y (lower-triangular matvec, N padded; y has N entries with zeros in the padding); scratch: gpk_trmv_scratch_doubles(N) per problem
+size_t gpk_trmv_scratch_doubles(int N);
 int gpk_trmv_lower(gpk_handle h, const double* Li, int N, const double* y, double* z, double* scratch, int batch = 1);
 // a = Li^t * z
 int gpk_trmv_lower_t(gpk_handle h, const double* Li, int N, const double* z, double* a, int batch = 1);

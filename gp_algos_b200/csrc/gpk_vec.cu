@@ -7,7 +7,7 @@
 
 namespace {
 
-constexpr int KCH = 1024;  // k-chunk of the split-k lower matvec
+constexpr int KCH = 256;   // k-chunk of the split-k lower matvec (short chunks: ~2000 CTAs at n = 8192 keep enough loads in flight)
 
 // partial[b][chunk][r] = sum_{k in chunk, k < rowblock_end} Li_b[r + k*N] * y_b[k]
 __global__ void __launch_bounds__(128) trmv_lower_partial(const double* __restrict__ Li, int N, const double* __restrict__ y,
@@ -25,12 +25,12 @@ __global__ void __launch_bounds__(128) trmv_lower_partial(const double* __restri
     const double* col = Li + r + (int64_t)k0 * N;
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     int k = k0;
-    for (; k + 3 < k1; k += 4) {
-        a0 += col[0] * y[k];
-        a1 += col[N] * y[k + 1];
-        a2 += col[2 * (int64_t)N] * y[k + 2];
-        a3 += col[3 * (int64_t)N] * y[k + 3];
-        col += 4 * (int64_t)N;
+    for (; k + 7 < k1; k += 8) {
+        const double m0 = col[0], m1 = col[N], m2 = col[2 * (int64_t)N], m3 = col[3 * (int64_t)N];
+        const double m4 = col[4 * (int64_t)N], m5 = col[5 * (int64_t)N], m6 = col[6 * (int64_t)N], m7 = col[7 * (int64_t)N];
+        a0 += m0 * y[k];     a1 += m1 * y[k + 1]; a2 += m2 * y[k + 2]; a3 += m3 * y[k + 3];
+        a0 += m4 * y[k + 4]; a1 += m5 * y[k + 5]; a2 += m6 * y[k + 6]; a3 += m7 * y[k + 7];
+        col += 8 * (int64_t)N;
     }
     for (; k < k1; ++k) { a0 += col[0] * y[k]; col += N; }
     partial[(int64_t)ch * N + r] = (a0 + a1) + (a2 + a3);
@@ -221,6 +221,8 @@ int gpk_trmv_lower_t(gpk_handle h, const double* Li, int N, const double* z, dou
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }
+
+size_t gpk_trmv_scratch_doubles(int N) { return (size_t)((N + KCH - 1) / KCH) * N; }
 
 int gpk_colwise_dot(gpk_handle h, const double* M, int64_t ld, int rows, int cols, const double* v, double* out, int square,
                     int batch, int64_t strideM, int64_t strideV, int64_t strideOut) {
