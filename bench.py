@@ -258,8 +258,8 @@ def run_gpk(args):
                               f"n={nn}, k={kk})", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": ach / peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel and shape from the ncu --set full capture in
-                    # profiles/r01_ncu_summary_v2.txt (628.4 + 59.3 MB; algorithmic 268 MB), bytes per launch
-                    "traffic": 687.69e6 if (nn, kk) == (4096, 4096) else None,
+                    # profiles/r01_ncu_summary_v3.txt (608.4 + 60.3 MB; algorithmic 268 MB), bytes per launch
+                    "traffic": 668.71e6 if (nn, kk) == (4096, 4096) else None,
                     "peak_source": f"cuBLAS Dgemm {n}^3 measured live in this run (MEASURED_PEAKS.json has no FP64 entry; "
                                    "DMMA pipe ceiling 37.1 TFLOP/s, profiles/r01_fp64_microbench.txt)",
                     "eval_flops": float(n) ** 3, "eval_tflops": float(n) ** 3 / (ms / args.steps) * 1e-9,

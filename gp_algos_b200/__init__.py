@@ -8,6 +8,7 @@ and error behaviour), used by the parity tests and the benchmark:
     utils.MatrixUtils       ->  gp_algos_b200.matrix_utils       (buildKernelMatrix, forwardSolve, ...)
     gp.regression.GpPredictor -> gp_algos_b200.gp_predictor      (GpPredictor, PredictionInput, ...)
     gp.classification.*      ->  gp_algos_b200.ep_classification (EpParameterEstimator, GpClassifier, ...)
+    dynamicalsystems.filtering.{UnscentedKalmanFilter, GPUnscentedKalmanFilter} -> gp_algos_b200.gp_ukf
     gp.optimization.GPOptimizer -> gp_algos_b200.gp_optimizer    (GP-UCB inner loop on a resident model)
     (batched independent GPs and their rank sharding: gp_algos_b200.batched;
      one large GP over a 2-D block-cyclic GPU grid: gp_algos_b200.distributed)
@@ -23,6 +24,8 @@ from .ep_classification import (EpParameterEstimator, GpClassifier, MarginalLike
                                 AvgBasedStopCriterion, FixedSweeps, ClassifierInput, AfterEstimationClassifierInput,
                                 HyperParameterOptimInput)
 from .gp_optimizer import GPOptimizer, GPOInput, BreezeLbfgsOptimizer, ucb_with_gradient  # noqa: F401
+from .gp_ukf import (UnscentedKalmanFilter, GPUnscentedKalmanFilter, UnscentedTransformParams, UnscentedFilteringInput,  # noqa: F401
+                     SsmModel, FilteringOutput)
 from ._lib import GpkError, NotPositiveDefiniteError, MatrixNotSymmetricError, lib_path  # noqa: F401
 
 __all__ = ["GaussianRbfKernel", "GaussianRbfParams", "GpPredictor", "PredictionInput", "PredictionTrainingInput",

@@ -565,6 +565,93 @@ def fast_ep_loglik_derivs(X, theta, K, tau, nu, L):
     return g
 
 
+# --------------------------------------------------------------------------------------------
+# GP-UKF (dynamicalsystems/filtering/UnscentedKalmanFilter.scala, GPUnscentedKalmanFilter.scala): restated per sigma
+# point and per output dimension exactly like the reference drives GpPredictor.computePosterior (m = 1 every time).
+# --------------------------------------------------------------------------------------------
+def ukf_unscented_transform(mean, cov, alpha, beta, kappa, func):
+    """UKF:82-118 -> (finalMean, finalCov, (w_0_m, w_0_c, w_i_c), sigmaPoints, transformedSigmaPoints); func: vector -> vector."""
+    mean = np.asarray(mean, dtype=np.float64); cov = np.asarray(cov, dtype=np.float64)
+    d = len(mean)
+    L = np.linalg.cholesky(cov)
+    lam = alpha * alpha * (d + kappa) - d
+    sp = np.zeros((2 * d + 1, d)); sp[0] = mean
+    for col in range(d):
+        c = L[:, col] * math.sqrt(d + lam)
+        sp[col + 1] = mean + c
+        sp[col + 1 + d] = mean - c
+    w0m = lam / (d + lam); w0c = (lam / (d + lam)) + (1 - alpha * alpha + beta); wic = 1 / (2 * (d + lam))
+    first = np.asarray(func(sp[0]), dtype=np.float64)
+    tsp = np.zeros((2 * d + 1, len(first))); tsp[0] = first
+    fm = first * w0m
+    for i in range(1, 2 * d + 1):
+        tsp[i] = func(sp[i])
+        fm = fm + tsp[i] * wic
+    diff = tsp[0] - fm
+    fc = np.outer(diff, diff) * w0c
+    for i in range(1, 2 * d + 1):
+        diff = tsp[i] - fm
+        fc = fc + np.outer(diff, diff) * wic
+    return fm, fc, (w0m, w0c, wic), sp, tsp
+
+
+def _log_gaussian_density(at, means, covs):
+    """StatsUtils.scala:45-56."""
+    d = len(means)
+    diff = np.asarray(at) - np.asarray(means)
+    sign, logdet = np.linalg.slogdet(covs)
+    dens = (2 * math.pi) ** (-0.5 * d) * (sign * math.exp(logdet)) ** -0.5 * math.exp(-0.5 * float(diff @ np.linalg.solve(covs, diff)))
+    return math.log(dens) if dens > 0 else -math.inf
+
+
+def gpukf_infer(hidden, observations, theta, init_mean, init_cov, alpha=1.0, beta=0.0, kappa=2.0):
+    """GPUKF:63-147 (learn one GP per state / observation dimension with fixed hyper-parameters) + UKF:24-80.
+    hidden: d_state x tMax sampled trajectory, observations: d_obs x tMax.  -> (hiddenMeans, hiddenCovs[list], ll)."""
+    hidden = np.asarray(hidden, dtype=np.float64); obs = np.asarray(observations, dtype=np.float64)
+    Xall = np.ascontiguousarray(hidden.T); Xprev = np.ascontiguousarray(Xall[:-1])
+    diffs = hidden[:, 1:] - hidden[:, :-1]
+    sys_lc = [fast_precompute(Xprev, diffs[dim], theta) for dim in range(hidden.shape[0])]      # GPUKF:105-121
+    obs_lc = [fast_precompute(Xall, obs[dim], theta) for dim in range(obs.shape[0])]
+
+    def post(X, lc, x):                                                                           # computePosterior, m = 1
+        m, S, _ = fast_compute_posterior(X, np.asarray(x, dtype=np.float64).reshape(1, -1), lc[0], lc[1], theta)
+        return m[0], S[0, 0]
+
+    trans = lambda p: np.asarray(p) + np.array([post(Xprev, lc, p)[0] for lc in sys_lc])         # GPUKF:77-83
+    obsf = lambda p: np.array([post(Xall, lc, p)[0] for lc in obs_lc])                           # GPUKF:84-90
+    tMax, hid = obs.shape[1], len(init_mean)
+    means = np.zeros((hid, tMax)); covs = [None] * tMax
+    means[:, 0] = init_mean; covs[0] = np.asarray(init_cov, dtype=np.float64)
+    ll = 0.0
+    for t in range(1, tMax):                                                                       # UKF:38-78
+        m1, c1, w, _, zT = ukf_unscented_transform(means[:, t - 1], covs[t - 1], alpha, beta, kappa, trans)
+        Q = np.diag([post(Xprev, lc, means[:, t - 1])[1] for lc in sys_lc])                      # GPUKF:95-98
+        mz, cz = m1, c1 + Q
+        m2, c2, _, _, yT = ukf_unscented_transform(mz, cz, alpha, beta, kappa, obsf)
+        R = np.diag([post(Xall, lc, m1)[1] for lc in obs_lc])                                    # GPUKF:99-102
+        my, S = m2, c2 + R
+        zy = np.outer(zT[0] - mz, yT[0] - my) * w[1]
+        for i in range(1, 2 * hid + 1):
+            zy = zy + np.outer(zT[i] - mz, yT[i] - my) * w[2]
+        K = zy @ np.linalg.inv(S)
+        means[:, t] = mz + K @ (obs[:, t] - my)
+        covs[t] = cz - (K @ S) @ K.T
+        ll += _log_gaussian_density(obs[:, t], my, S)
+    return means, covs, ll
+
+
+def make_ssm_series(tMax=80, seed=7):
+    """A small nonlinear 2-state / 2-observation state-space series for the GP-UKF tests (synthetic, seeded)."""
+    rng = np.random.default_rng(seed)
+    h = np.zeros((2, tMax)); o = np.zeros((2, tMax))
+    h[:, 0] = rng.standard_normal(2) * 0.5
+    for t in range(tMax):
+        o[:, t] = np.array([np.sin(h[0, t]) + 0.5 * h[1, t], 0.3 * h[0, t] * h[1, t] + h[1, t]]) + 0.05 * rng.standard_normal(2)
+        if t + 1 < tMax:
+            h[:, t + 1] = np.array([0.9 * h[0, t] + 0.2 * np.sin(h[1, t]), 0.8 * h[1, t] + 0.3 * np.cos(h[0, t])]) + 0.1 * rng.standard_normal(2)
+    return h, o
+
+
 def make_c1(n=1000, m=500, seed=1):
     rng = np.random.default_rng(seed)
     x = rng.uniform(0, 10, size=(n, 1))
