@@ -109,6 +109,13 @@ def test_cholesky_error_behaviour():
         MU.cholesky(A)
     assert e.value.minor == 201
     assert np.allclose(MU.cholesky(np.eye(5) * 4.0), np.eye(5) * 2.0)  # handle stays usable after an error
+    # same through the look-ahead (pipelined) driver, which takes over at padded N >= 4096: the failing minor sits in
+    # the 6th block column and every stream must drain cleanly
+    B = np.eye(4500); B[2900, 2900] = -3.0
+    with pytest.raises(gp.NotPositiveDefiniteError) as e:
+        MU.cholesky(B)
+    assert e.value.minor == 2901
+    assert np.allclose(MU.cholesky(np.eye(4200) * 9.0), np.eye(4200) * 3.0)
 
 
 # ---- triangular solves / inverse -------------------------------------------------------------------------
