@@ -125,9 +125,14 @@ class GpuBlockOps:
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         # a non-default stream: the handle, torch copies and the NCCL hand-offs all order on it
-        self.stream = torch.cuda.Stream(self.device)
+        self.stream = torch.cuda.Stream(self.device, priority=-1)
         self.handle = _lib.Handle(device, stream=self.stream.cuda_stream)
         self.lib = self.handle.lib
+        # auxiliary lanes: the bulk of a trailing update is spread over two more streams, so the partial last wave of one
+        # block-column GEMM is filled by the next one (a lane has its own handle because a handle is bound to one stream)
+        self.naux = 2
+        self.aux_streams = [torch.cuda.Stream(self.device) for _ in range(self.naux)]
+        self.aux_handles = [_lib.Handle(device, stream=st.cuda_stream) for st in self.aux_streams]
 
     # -- memory ---------------------------------------------------------------------------------------------
     def alloc(self, count: int, zero: bool = False):
@@ -168,9 +173,21 @@ class GpuBlockOps:
     def sum_log_diag(self, A: Mat, n: int, out: Vec, accumulate: bool):
         self.handle.check(self.lib.gpk_sum_log_diag_dev(self.handle.h, self._pm(A), A.ld, n, self._p(out.buf, out.off), int(accumulate)))
 
-    def gemm_nt(self, m: int, p: int, k: int, alpha: float, P: Mat, Q: Mat, beta: float, Cm: Mat, q_lower_tri: bool = False):
-        self.handle.check(self.lib.gpk_gemm_nt_dev(self.handle.h, m, p, k, float(alpha), self._pm(P), P.ld, self._pm(Q), Q.ld,
-                                                   float(beta), self._pm(Cm), Cm.ld, int(q_lower_tri)))
+    def gemm_nt(self, m: int, p: int, k: int, alpha: float, P: Mat, Q: Mat, beta: float, Cm: Mat, q_lower_tri: bool = False,
+                lane: Optional[int] = None):
+        hd = self.handle if lane is None else self.aux_handles[lane]
+        hd.check(self.lib.gpk_gemm_nt_dev(hd.h, m, p, k, float(alpha), self._pm(P), P.ld, self._pm(Q), Q.ld,
+                                          float(beta), self._pm(Cm), Cm.ld, int(q_lower_tri)))
+
+    # -- stream plumbing for the auxiliary lanes (lane None = the main stream) ----------------------------------
+    def record(self, lane: Optional[int] = None):
+        ev = self.torch.cuda.Event()
+        ev.record(self.stream if lane is None else self.aux_streams[lane])
+        return ev
+
+    def wait(self, ev, lane: Optional[int] = None):
+        if ev is not None:
+            (self.stream if lane is None else self.aux_streams[lane]).wait_event(ev)
 
     def gemv(self, trans: bool, m: int, ncols: int, alpha: float, M: Mat, x: Vec, beta: float, y: Vec):
         self.handle.check(self.lib.gpk_gemv_dev(self.handle.h, int(trans), m, ncols, float(alpha), self._pm(M), M.ld,
@@ -271,7 +288,9 @@ class DistributedGp:
                 self.A = Mat(ops.alloc(mloc * cloc), 0, max(mloc, 1))
             A = self.A = Mat(self.A.buf, 0, max(mloc, 1))
             self.Li = ops.alloc(nt * nb * nb, zero=True)          # every L_kk^-1, replicated (back solve)
-            panel = [ops.alloc(max(nt - 1, 1) * nb * nb) for _ in range(2)]
+            naux = getattr(ops, "naux", 0)
+            NP = 3 if naux else 2                                 # panel buffers: with lanes a panel is read one step longer
+            panel = [ops.alloc(max(nt - 1, 1) * nb * nb) for _ in range(NP)]
             Dbuf = Mat(ops.alloc(nb * nb), 0, nb)
             info = ops.alloc_int(nt)
             scal = ops.alloc(4, zero=True)                        # [sum log L_ii, y.alpha]
@@ -317,7 +336,7 @@ class DistributedGp:
                     ops.sum_log_diag(Dbuf, nb, Vec(scal, 0), True)
                 works = [self._bcast(self.Li[k * nb * nb:(k + 1) * nb * nb], g.rank_of(oq, oc))]
                 first, cnt, off = g.panel_layout(k)
-                pbuf = panel[k % 2]
+                pbuf = panel[k % NP]
                 if g.pc == oc and cnt[g.pr]:
                     self._wait(works)
                     rows = cnt[g.pr] * nb
@@ -332,11 +351,13 @@ class DistributedGp:
 
             my_cols = list(g.col_blocks())
             pend = factor_panel(0)
+            step_done = {}                 # k -> events closing the lanes' work of step k
+            next_col_ready = None          # this rank's block column k+1 has received update k-1 (issued first on its lane)
             for k in range(nt):
                 self._wait(pend)
                 pend = []
                 first, cnt, off = g.panel_layout(k)
-                pbuf = panel[k % 2]
+                pbuf = panel[k % NP]
                 Li_k = Mat(self.Li, k * nb * nb, nb)
                 # forward substitution, replicated: z_k = L_kk^-1 y_k ; y_i -= L_ik z_k  (MatrixUtils.scala:17-21)
                 zk = Vec(z, k * nb)
@@ -345,21 +366,45 @@ class DistributedGp:
                     if cnt[q]:
                         ops.gemv(False, cnt[q] * nb, nb, -1.0, Mat(pbuf, off[q] * nb * nb, cnt[q] * nb), zk, 1.0,
                                  yq[q].at((first[q] // g.Pr) * nb))
+                if naux:
+                    ev_panel = ops.record()                       # panel k has arrived (the main stream waited for NCCL)
+                    for lane in range(naux):
+                        ops.wait(ev_panel, lane)
+                    for ev in step_done.pop(k - 2, []):           # panel buffer (k+1) % 3 was last read by the lanes at step k-2
+                        ops.wait(ev)
                 if k + 1 < nt and g.pc != (k + 1) % g.Pc:
                     pend = factor_panel(k + 1)        # not in the next panel's process column: just join its broadcasts
+                col_ready, new_ready = next_col_ready, None
                 for j in my_cols:
                     if j <= k:
                         continue
+                    # column k+1 stays on the main stream (its panel is factored right behind it); the rest alternate lanes,
+                    # a block column always on the same lane so that its successive updates stay ordered
+                    lane = None if (j == k + 1 or not naux) else (j // g.Pc) % naux
                     i0 = first_at_least(j, g.pr, g.Pr)
                     if i0 < nt:
                         rows = (g.nrow_blocks - i0 // g.Pr) * nb
                         left = Mat(pbuf, off[g.pr] * nb * nb + ((i0 - first[g.pr]) // g.Pr) * nb, cnt[g.pr] * nb)
                         qj = j % g.Pr
                         right = Mat(pbuf, off[qj] * nb * nb + ((j - first[qj]) // g.Pr) * nb, cnt[qj] * nb)
-                        ops.gemm_nt(rows, nb, nb, -1.0, left, right, 1.0, A.at((i0 // g.Pr) * nb, (j // g.Pc) * nb))
+                        if naux and j == k + 1:
+                            ops.wait(col_ready)                   # update k-1 of this column ran on a lane
+                        if naux:
+                            ops.gemm_nt(rows, nb, nb, -1.0, left, right, 1.0, A.at((i0 // g.Pr) * nb, (j // g.Pc) * nb), lane=lane)
+                        else:
+                            ops.gemm_nt(rows, nb, nb, -1.0, left, right, 1.0, A.at((i0 // g.Pr) * nb, (j // g.Pc) * nb))
                         self.launch_gemm += 1
+                        if naux and j == k + 2:
+                            new_ready = ops.record(lane)          # first job of its lane in this step: next step's look-ahead waits on it
                     if j == k + 1:
                         pend = factor_panel(k + 1)    # look-ahead: panel k+1 goes on the wire before the rest of the update
+                next_col_ready = new_ready
+                if naux:
+                    step_done[k] = [ops.record(lane) for lane in range(naux)]
+            if naux:
+                for evs in step_done.values():
+                    for ev in evs:
+                        ops.wait(ev)
 
             # ---- back solve L^T alpha = z (MatrixUtils.scala:23-27), block columns in reverse --------------------
             alpha = ops.alloc(npad, zero=True)
