@@ -26,7 +26,7 @@ void* gpk_arena(gpk_handle h, int which, size_t bytes) {
     if (h->arena[which]) {
         cudaStreamSynchronize(h->stream);
         for (int i = 0; i < GPK_NSIDE; ++i) cudaStreamSynchronize(h->side[i]);
-        for (int i = 0; i < 2; ++i) cudaStreamSynchronize(h->pipe[i]);
+        for (int i = 0; i < GPK_NPIPE; ++i) cudaStreamSynchronize(h->pipe[i]);
         cudaFree(h->arena[which]);
         h->arena[which] = nullptr;
         h->arena_bytes[which] = 0;
@@ -109,7 +109,7 @@ int gpk_create(gpk_handle* out, int device, void* stream) {
     const int sideprio = (mainprio < least && least - 1 >= greatest) ? least - 1 : least;
     for (int i = 0; i < GPK_NSIDE; ++i)
         if (cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, sideprio) != cudaSuccess) { delete h; return GPK_ECUDA; }
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < GPK_NPIPE; ++i)
         if (cudaStreamCreateWithPriority(&h->pipe[i], cudaStreamNonBlocking, least) != cudaSuccess) { delete h; return GPK_ECUDA; }
     for (int i = 0; i < GPK_NEVENTS; ++i)
         if (cudaEventCreateWithFlags(&h->evpool[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return GPK_ECUDA; }
@@ -123,7 +123,7 @@ int gpk_destroy(gpk_handle h) {
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < GPK_NSIDE; ++i)
         if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < GPK_NPIPE; ++i)
         if (h->pipe[i]) { cudaStreamSynchronize(h->pipe[i]); cudaStreamDestroy(h->pipe[i]); }
     for (int i = 0; i < GPK_NARENA; ++i)
         if (h->arena[i]) cudaFree(h->arena[i]);

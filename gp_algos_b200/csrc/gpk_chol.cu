@@ -197,6 +197,25 @@ namespace {
 
 inline cudaEvent_t next_event(gpk_handle h) { return h->evpool[h->ev_next++ % GPK_NEVENTS]; }
 
+// GPK_TRACE=1: timed events at the milestones of the pipelined driver, printed (ms since its start) after a device sync.
+// Debug aid only (it serialises the call with the host); off by default.
+struct Trace {
+    struct Mark { cudaEvent_t ev; char what[24]; };
+    bool on; cudaEvent_t t0; Mark m[512]; int n;
+    Trace() : on(false), t0(nullptr), n(0) { const char* e = getenv("GPK_TRACE"); on = e && atoi(e) > 0; }
+    void start(cudaStream_t s) { if (!on) return; cudaEventCreate(&t0); cudaEventRecord(t0, s); }
+    void mark(cudaStream_t s, const char* tag, int k) {
+        if (!on || n >= 512) return;
+        cudaEventCreate(&m[n].ev); cudaEventRecord(m[n].ev, s); snprintf(m[n].what, sizeof(m[n].what), "%s%d", tag, k); ++n;
+    }
+    void dump() {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        for (int i = 0; i < n; ++i) { float ms = 0; cudaEventElapsedTime(&ms, t0, m[i].ev); fprintf(stderr, "[gpk trace] %-10s %8.3f ms\n", m[i].what, ms); cudaEventDestroy(m[i].ev); }
+        cudaEventDestroy(t0);
+    }
+};
+
 // block column jc (rows >= its own start) -= L_{:,k} L_{jc,k}^t, L staged in Li's slots; lower tiles of the diagonal block only
 int col_update(gpk_handle h, double* A, const double* Li, int N, int bk, int sk, int bj, int sj) {
     GemmDesc g = gemm_desc();
@@ -218,20 +237,24 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     Ctx c{h, N, N, keep_L, info_dev, 1, (int64_t)N * N, 0};
     double* Tdiag = T;
     double* Trow = T + rec_scratch_doubles(nbk);
-    cudaStream_t M = h->stream, S = h->pipe[0], S2 = h->pipe[1];
+    cudaStream_t M = h->stream, S = h->pipe[0], S2 = h->pipe[1], S3 = h->pipe[2];
     cudaEvent_t ev = next_event(h);
     GPK_CUDA(h, cudaEventRecord(ev, M));            // K is built (and earlier users of the buffers are done) before S/S2 start
     GPK_CUDA(h, cudaStreamWaitEvent(S, ev, 0));
     GPK_CUDA(h, cudaStreamWaitEvent(S2, ev, 0));
+    GPK_CUDA(h, cudaStreamWaitEvent(S3, ev, 0));
     cudaEvent_t evGcol_prev = nullptr;              // S finished block column k+1 of trailing update k-1
     cudaEvent_t evLi = nullptr;                     // S2 finished the last row of L^-1
     int rc;
+    Trace tr;
+    tr.start(M);
     for (int k = 0; k < nt; ++k) {
         const int bk = bs(k), sk = bs(k + 1) - bk;
         rc = potrf_inv_rec(c, A + bk + (int64_t)bk * N, Li + bk + (int64_t)bk * N, Tdiag, sk, bk, 0);              // F_k
         if (rc) return rc;
         cudaEvent_t evF = next_event(h);
         GPK_CUDA(h, cudaEventRecord(evF, M));
+        tr.mark(M, "M:F", k);
         if (k + 1 < nt) {
             const int b1 = bs(k + 1), s1 = bs(k + 2) - b1;
             GemmDesc g = gemm_desc();                                                                                // P_k
@@ -248,8 +271,10 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
             cudaEvent_t evE = next_event(h);
             GPK_CUDA(h, cudaEventRecord(evE, M));
             if (evGcol_prev) GPK_CUDA(h, cudaStreamWaitEvent(M, evGcol_prev, 0));
+            tr.mark(M, "M:P", k);
             rc = col_update(h, A, Li, N, bk, sk, b1, s1);                                                            // U_k(:,k+1)
             if (rc) return rc;
+            tr.mark(M, "M:Ucol", k);
             evGcol_prev = nullptr;
             if (k + 2 < nt) {
                 GPK_CUDA(h, cudaStreamWaitEvent(S, evE, 0));
@@ -264,6 +289,7 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
                     rc = col_update(h, A, Li, N, bk, sk, b3, N - b3);                                                // U_k(k+3:, k+3:)
                     if (rc) return rc;
                 }
+                tr.mark(S, "S:U", k);
             }
         }
         GPK_CUDA(h, cudaStreamWaitEvent(S2, evF, 0));
@@ -275,11 +301,18 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
             rc = gemm_Li21(c, Trow, Likk, Li + bk, bk, sk);                       // Li_{k,0:k} = -Li_kk T_k
             if (rc) return rc;
         }
+        tr.mark(S2, "S2:R", k);
         if (k == nt - 1) {                                                        // L^-1 is complete
             evLi = next_event(h);
             GPK_CUDA(h, cudaEventRecord(evLi, S2));
         }
         if (Kinv) {
+            // the K^-1 contribution of row k only needs row k of L^-1: it runs on its own stream so that the row chain on S2
+            // (which every later row waits for) is not queued behind these larger GEMMs
+            cudaEvent_t evR = next_event(h);
+            GPK_CUDA(h, cudaEventRecord(evR, S2));
+            GPK_CUDA(h, cudaStreamWaitEvent(S3, evR, 0));
+            StreamSwap sw3(h, S3);
             GemmDesc g;
             if (k > 0) {
                 g = gemm_desc();                                                  // Kinv[k,0:k] = Li_kk^t Li_{k,0:k}
@@ -305,13 +338,18 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
             }
         }
     }
+    tr.mark(S3, "S3:Q", nt - 1);
+    tr.dump();
     // join: the caller's stream continues once L and L^-1 are complete.  With kinv_done != nullptr the K^-1 accumulation of
     // the last row (the largest) keeps running on S2 and the caller waits for *kinv_done only where it reads K^-1, so
     // alpha = L^-t L^-1 y and the log-likelihood overlap it.
     cudaEvent_t e1 = next_event(h), e2 = next_event(h);
     GPK_CUDA(h, cudaEventRecord(e1, S));
-    GPK_CUDA(h, cudaEventRecord(e2, S2));
+    GPK_CUDA(h, cudaEventRecord(e2, S3));
     GPK_CUDA(h, cudaStreamWaitEvent(M, e1, 0));
+    if (!Kinv) {                                   // no K^-1 requested: S3 idle, join the row chain
+        GPK_CUDA(h, cudaEventRecord(e2, S2));
+    }
     if (kinv_done && Kinv && evLi) {
         GPK_CUDA(h, cudaStreamWaitEvent(M, evLi, 0));
         *kinv_done = e2;

@@ -8,6 +8,7 @@
 #include "../../include/gpk.h"
 
 #define GPK_TILE 128
+#define GPK_NPIPE 3
 #define GPK_NSIDE 4      // side streams (one per recursion depth, cyclic)
 #define GPK_NEVENTS 256  // fork/join event pool (cyclic)  // every internal matrix dimension / leading dimension is a multiple of this
 
@@ -16,7 +17,7 @@ struct gpk_handle_s {
     cudaStream_t stream;
     bool own_stream;
     cudaStream_t side[GPK_NSIDE];
-    cudaStream_t pipe[2];    // lowest-priority streams of the pipelined factorisation (trailing updates; inverse rows + K^-1)
+    cudaStream_t pipe[GPK_NPIPE];   // lowest-priority streams of the pipelined factorisation (trailing updates; inverse rows; K^-1)
     cudaEvent_t evpool[GPK_NEVENTS];
     unsigned ev_next;
     // grow-only device arenas (A: factor / K^-1, B: L^-1, T: GEMM scratch, misc: small vectors)
