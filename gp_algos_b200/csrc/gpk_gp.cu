@@ -425,13 +425,16 @@ int gpk_gp_model_predict(gpk_handle h, gpk_model m, const double* Xs, int ms, in
     // mean = K* alpha (GpPredictor.scala:54)
     rc = gpk_colwise_dot(h, dKsT, N, N, ms, m->alpha, dMean, 0);
     if (rc) return rc;
-    // V = L^-1 K*^t (GpPredictor.scala:55): C(i,c) = sum_{k<=i} Li(i,k) KsT(k,c)
+    // V = L^-1 K*^t (GpPredictor.scala:55): C(i,c) = sum_{k<=i} Li(i,k) KsT(k,c).  Skipped when only the mean is wanted
+    // (the GP-UKF transition / observation functions, GPUnscentedKalmanFilter.scala:77-90, read nothing else).
     GemmDesc g = gemm_desc();
-    g.P = dKsT; g.ldp = N; g.p_kcontig = 1;
-    g.Q = m->Li; g.ldq = N; g.q_kcontig = 0;
-    g.D = dV; g.ldd = N; g.R = M; g.S = N; g.K = N; g.ke_s = 1; g.heavy_last = 1;
-    rc = gpk_gemm(h, g);
-    if (rc) return rc;
+    if (sigma || V) {
+        g.P = dKsT; g.ldp = N; g.p_kcontig = 1;
+        g.Q = m->Li; g.ldq = N; g.q_kcontig = 0;
+        g.D = dV; g.ldd = N; g.R = M; g.S = N; g.K = N; g.ke_s = 1; g.heavy_last = 1;
+        rc = gpk_gemm(h, g);
+        if (rc) return rc;
+    }
     if (mean) GPK_CUDA(h, cudaMemcpyAsync(mean, dMean, (size_t)ms * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (sigma) {
         if (want_full_cov) {

@@ -213,6 +213,16 @@ class FittedGp:
             _lib.ptr(V) if want_v else None, self.n))
         return GaussianDistribution(mean, sigma), V
 
+    def mean(self, testData) -> np.ndarray:
+        """Posterior mean only: K* alpha (GpPredictor.scala:53-54), no triangular work -- what the GP-UKF transition and
+        observation functions read from computePosterior (GPUnscentedKalmanFilter.scala:77-90)."""
+        Xs = _lib.fmat(np.atleast_2d(testData))
+        m = Xs.shape[0]
+        mean = np.empty(m)
+        self.handle.check(self.handle.lib.gpk_gp_model_predict(self.handle.h, self._m, _lib.ptr(Xs), m, m, 0, _lib.ptr(mean), None, m,
+                                                               None, self.n))
+        return mean
+
     @property
     def alphaVec(self) -> np.ndarray:
         a = np.empty(self.n)

@@ -200,7 +200,7 @@ class GPUnscentedKalmanFilter(UnscentedKalmanFilter):
 
         def means(models, pts):
             pts = np.atleast_2d(np.asarray(pts, dtype=np.float64))
-            return np.stack([m.computePosterior(pts, full_cov=False, want_v=False)[0].mean for m in models], axis=1)
+            return np.stack([m.mean(pts) for m in models], axis=1)
 
         def noise(models, point):                                                    # :138-147: diag of sigma(0,0) per dimension
             pt = np.atleast_2d(np.asarray(point, dtype=np.float64))

@@ -38,5 +38,7 @@ def test_gp_ukf_models_are_released_and_predictions_batch_consistently():
     single = np.stack([model.transitionFuncImpl(None, p, 1)[0] for p in pts])
     assert np.allclose(batch, single, rtol=1e-12, atol=1e-14)      # 2d+1 sigma points in one call == one call per point
     assert len(ukf._models) == 4
+    for mdl in ukf._models:                                         # mean-only path == mean of the full posterior call
+        assert np.array_equal(mdl.mean(pts), mdl.computePosterior(pts, full_cov=False, want_v=False)[0].mean)
     ukf.close()
     assert ukf._models == []
