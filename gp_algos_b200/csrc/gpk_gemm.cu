@@ -5,13 +5,16 @@
 //
 // sm_100a has no tcgen05 kind for f64 (ptxas rejects .kind::f64), so the FP64 tensor path is the
 // warp-level mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4.  Measured on B200 (profiles/r01_fp64_microbench.txt):
-// DMMA and DFMA both peak at 37.1 TFLOP/s; DMMA needs 4x fewer shared-memory operand bytes per flop,
-// which is what lets a 128x128x16 CTA tile with 64x32 warp tiles run pipe-bound.
+// DMMA and DFMA both peak at 37.1 TFLOP/s; DMMA needs 4x fewer shared-memory operand bytes per flop, which is what lets
+// a small CTA tile run pipe-bound.
 //
-// Layout: 256 threads = 8 warps as 2 (r) x 4 (s); each warp owns a 64 x 32 sub-tile = 8 x 4 DMMA
-// accumulators (128 registers/thread).  Operands are staged global -> shared with 16-byte cp.async
-// (LDGSTS) through a 4-stage ring; shared rows are padded by 4 doubles so that the 8-byte fragment
-// reads of a half-warp (4 k x 4 rows) hit 16 distinct bank pairs.
+// Default layout (SmallTile): 64 x 64 x 16 CTA tile, 128 threads = 4 warps as 2 (r) x 2 (s), each warp owning a 32 x 32
+// sub-tile = 4 x 4 DMMA accumulators; 3 CTAs per SM (60 KB of shared memory each), which beat every larger tile shape
+// (profiles/r01_tile_configs.txt).  Operands are staged global -> shared with 16-byte cp.async (LDGSTS) through a 3-stage
+// ring; shared rows are padded by 4 doubles so that the 8-byte fragment reads of a half-warp (4 k x 4 rows) hit 16 distinct
+// bank pairs.  The main loop carries running global pointers and cycling stage counters and issues the next refill behind
+// the first DMMA group of each k-step.  Measured: 32.5 TFLOP/s on the SYRK of n = k = 4096 (91.7 % of cuBLAS Dgemm), DMMA
+// pipe 95 % of active cycles (profiles/r01_ncu_summary_v3.txt).
 #include "gpk_internal.cuh"
 
 #include <stdlib.h>
@@ -55,28 +58,6 @@ using BigTile = TileCfg<2, 4, 8, 4, 4, 1>;
 using WideTile = TileCfg<4, 4, 4, 4, 4, 1>;    // 128 x 128 tile on 16 warps of 32 x 32 (4 warps per scheduler)
 using MidTile = TileCfg<2, 2, 8, 4, 3, 2>;     // 128 x 64 tile, 4 warps of 64 x 32, 2 CTAs per SM
 using SmallTile = TileCfg<2, 2, 4, 4, 3, 3>;   // 3 stages x 20 KB = 60 KB -> 3 CTAs (12 warps) per SM
-
-// stage a TX (x) by 16 (k) operand tile
-template <bool KC, int TX, int NT>
-__device__ __forceinline__ void load_tile(double* st, const double* g, int64_t ld, int x0, int k0, int tid) {
-    constexpr int PER_THREAD = TX * TK / 2 / NT;
-    constexpr int LDX = TX + 4;
-    if (!KC) {
-#pragma unroll
-        for (int i = 0; i < PER_THREAD; ++i) {
-            int c = tid + i * NT;
-            int k = c / (TX / 2), x = (c % (TX / 2)) * 2;
-            cp_async16(st + k * LDX + x, g + (int64_t)(k0 + k) * ld + (x0 + x));
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < PER_THREAD; ++i) {
-            int c = tid + i * NT;
-            int x = c >> 3, k = (c & 7) * 2;
-            cp_async16(st + x * LDK + k, g + (int64_t)(x0 + x) * ld + (k0 + k));
-        }
-    }
-}
 
 template <bool PK, bool QK, class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_BLOCKS) gemm_f64_dmma_kernel(const GemmDesc g) {
