@@ -208,3 +208,20 @@ def test_obtain_optimal_hyper_params_improves_the_likelihood():   # GpPredictor.
     assert abs(ll1 - llo) <= 1e-6 * abs(llo)
     dist, ll, hp = p.predictWithParamsOptimization(gp.PredictionInput(X, X[:5], None, y), True)
     assert abs(ll - ll1) <= 1e-9 * abs(ll1) and hp == best and dist.mean.shape == (5,)
+
+
+def test_maximum_feature_dimension_and_beyond():
+    """D = 64 is the widest ARD kernel the device kernels stage (GPK_MAX_D); one more is an argument error, not a crash."""
+    rng = np.random.default_rng(64)
+    n, D = 300, 64
+    X = rng.uniform(size=(n, D)); y = np.sin(X[:, 0] * 3) + 0.1 * rng.standard_normal(n)
+    th = orc.pack_theta(1.2, np.linspace(2.0, 4.0, D), 0.15)
+    ll, g = _pred(th).logLikelihoodWithDerivatives(gp.PredictionTrainingInput(X, None, y), th, D + 2)
+    llo, go = orc.fast_loglik_with_derivs(X, y, th)
+    assert abs(ll - llo) <= RTOL * abs(llo)
+    assert_grad(g, go)
+    K = gp.MatrixUtils.buildKernelMatrix(gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1])), X)
+    assert np.allclose(K, orc.fast_build_kernel_matrix(X, th), rtol=1e-13, atol=0)
+    X65 = rng.uniform(size=(50, 65)); th65 = orc.pack_theta(1.0, np.ones(65), 0.1)
+    with pytest.raises(ValueError):
+        _pred(th65).logLikelihoodWithDerivatives(gp.PredictionTrainingInput(X65, None, y[:50]), th65, 67)
