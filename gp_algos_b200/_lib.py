@@ -82,6 +82,7 @@ def load():
         lib.gpk_gp_model_destroy.argtypes = [vp, vp]
         lib.gpk_gp_model_get_alpha.argtypes = [vp, vp, vp]
         lib.gpk_gp_model_predict.argtypes = [vp, vp, vp, ci, _i64, ci, vp, vp, _i64, vp, _i64]
+        lib.gpk_gp_models_mean.argtypes = [vp, vp, ci, vp, ci, _i64, vp]
         lib.gpk_gp_model_ucb.argtypes = [vp, vp, vp, ci, _i64, cd, vp, vp, _i64, vp, vp]
         lib.gpk_gp_predict.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, _i64, vp, ci, cd, vp, vp, _i64, vp]
         lib.gpk_potrf_inv_block_dev.argtypes = [vp, vp, vp, ci, vp]

@@ -519,6 +519,37 @@ int gpk_gp_model_ucb(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_
     return gpk_synchronize(h);
 }
 
+// Posterior means of SEVERAL resident models at the same test rows in one call / one synchronisation: the GP-UKF step
+// (GPUnscentedKalmanFilter.scala:77-90: one GP per state / observation dimension, each asked for its mean at every sigma
+// point).  mean[j*ms + i] = mean of model j at row i.  Models may differ in training set, targets and hyper-parameters.
+int gpk_gp_models_mean(gpk_handle h, const gpk_model* models, int nmodels, const double* Xs, int ms, int64_t ldxs, double* mean) {
+    if (!h || !models || nmodels <= 0 || !Xs || ms <= 0 || ldxs < ms || !mean)
+        return gpk_set_error(h, GPK_EINVAL, "gpk_gp_models_mean: bad arguments");
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    const int D = models[0]->D, M = gpk_pad(ms);
+    int Nmax = 0;
+    for (int j = 0; j < nmodels; ++j) {
+        if (!models[j] || models[j]->D != D) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_models_mean: models disagree on D");
+        if (models[j]->N > Nmax) Nmax = models[j]->N;
+    }
+    ARENA_OR_FAIL(dXs, double*, h, ARENA_X, (size_t)ms * D * sizeof(double));
+    ARENA_OR_FAIL(buf, double*, h, ARENA_IO2, ((size_t)Nmax * M + (size_t)nmodels * M) * sizeof(double));
+    double* dKsT = buf;
+    double* dMean = buf + (size_t)Nmax * M;
+    int rc = gpk_upload_matrix(h, dXs, Xs, ms, D, ldxs);
+    if (rc) return rc;
+    for (int j = 0; j < nmodels; ++j) {
+        gpk_model m = models[j];
+        rc = gpk_cov_cross(h, m->X, m->n, m->n, dXs, ms, ms, m->pp.cp, dKsT, m->N, m->N, M);     // GpPredictor.scala:53
+        if (rc) return rc;
+        rc = gpk_colwise_dot(h, dKsT, m->N, m->N, ms, m->alpha, dMean + (size_t)j * M, 0);         // :54
+        if (rc) return rc;
+    }
+    GPK_CUDA(h, cudaMemcpy2DAsync(mean, (size_t)ms * sizeof(double), dMean, (size_t)M * sizeof(double), (size_t)ms * sizeof(double),
+                                  (size_t)nmodels, cudaMemcpyDeviceToHost, h->stream));
+    return gpk_synchronize(h);
+}
+
 int gpk_gp_predict(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y, const double* Xs, int ms,
                    int64_t ldxs, const double* theta, int has_s, double s, double* mean, double* sigma, int64_t lds, double* ll) {
     gpk_model m = nullptr;

@@ -172,6 +172,19 @@ class GpPredictor:
         return FittedGp.fit(self.handle, trainingData, targets, theta, sigmaNoise)
 
 
+def models_mean(models, testData) -> np.ndarray:
+    """Posterior means of several resident models at the same test rows in ONE device call -> (len(testData), len(models)).
+    The GP-UKF pattern: one GP per state / observation dimension, all sigma points at once
+    (GPUnscentedKalmanFilter.scala:77-90)."""
+    Xs = _lib.fmat(np.atleast_2d(testData))
+    m, k = Xs.shape[0], len(models)
+    h = models[0].handle
+    arr = (C.c_void_p * k)(*[mdl._m for mdl in models])
+    out = np.empty((k, m))
+    h.check(h.lib.gpk_gp_models_mean(h.h, arr, k, _lib.ptr(Xs), m, m, _lib.ptr(out)))
+    return out.T.copy()
+
+
 class FittedGp:
     """Opaque device token for (X, L^-1, alpha, theta) -- SURVEY.md 8(b) 'ownership'."""
 

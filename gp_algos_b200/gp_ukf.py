@@ -17,7 +17,7 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from .gp_predictor import FittedGp, GaussianDistribution, GpPredictor
+from .gp_predictor import FittedGp, GaussianDistribution, GpPredictor, models_mean
 
 
 @dataclass(frozen=True)
@@ -200,7 +200,7 @@ class GPUnscentedKalmanFilter(UnscentedKalmanFilter):
 
         def means(models, pts):
             pts = np.atleast_2d(np.asarray(pts, dtype=np.float64))
-            return np.stack([m.mean(pts) for m in models], axis=1)
+            return models_mean(models, pts)                                            # one device call for all dimensions
 
         def noise(models, point):                                                    # :138-147: diag of sigma(0,0) per dimension
             pt = np.atleast_2d(np.asarray(point, dtype=np.float64))

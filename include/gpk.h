@@ -126,6 +126,11 @@ int gpk_gp_model_get_alpha(gpk_handle h, gpk_model m, double* alpha);
  * The sigma diagonal includes noiseVar^2 (MatrixUtils.scala:63 via GpPredictor.scala:56). */
 int gpk_gp_model_predict(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_t ldxs,
                          int want_full_cov, double* mean, double* sigma, int64_t lds, double* V, int64_t ldv);
+/* Posterior means of nmodels resident models at the same ms test rows, one call and one synchronisation:
+ * mean[j*ms + i].  The GP-UKF step (GPUnscentedKalmanFilter.scala:77-90) asks one GP per state / observation dimension
+ * for its mean at every sigma point; the reference does that with (2d+1) x dims computePosterior calls. */
+int gpk_gp_models_mean(gpk_handle h, const gpk_model* models, int nmodels, const double* Xs, int ms, int64_t ldxs,
+                       double* mean);
 /* gp/optimization/GPOptimizer.scala:82-109 maximizeUCB's objective for ms candidate points (rows of Xs) at once:
  * ucb[i] = mean_i + k_param sqrt(sigma_i) and grad[i + d*ldg] = d ucb_i / d x_d
  *        = (dKs/dx) alpha + (0 - 2 (L^-1 dKs^t/dx)^t v) k_param / (2 sqrt(sigma_i)), Ks = k(x, X), v = L^-1 Ks^t

@@ -38,6 +38,9 @@ def test_gp_ukf_models_are_released_and_predictions_batch_consistently():
     single = np.stack([model.transitionFuncImpl(None, p, 1)[0] for p in pts])
     assert np.allclose(batch, single, rtol=1e-12, atol=1e-14)      # 2d+1 sigma points in one call == one call per point
     assert len(ukf._models) == 4
+    from gp_algos_b200.gp_predictor import models_mean
+    allm = models_mean(ukf._models[:2], pts)                        # every dimension in one call == one call per model
+    assert np.array_equal(allm, np.stack([mdl.mean(pts) for mdl in ukf._models[:2]], axis=1))
     for mdl in ukf._models:                                         # mean-only path == mean of the full posterior call
         assert np.array_equal(mdl.mean(pts), mdl.computePosterior(pts, full_cov=False, want_v=False)[0].mean)
     ukf.close()

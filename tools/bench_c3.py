@@ -28,4 +28,12 @@ t0 = time.perf_counter(); orc.fast_ep_estimate(Ks_, ts_, fixed_sweeps=1); t_cpu 
 res["cpu_port_one_sweep_n1024_s"] = t_cpu
 res["cpu_port_extrapolated_s_per_sweep_n4096"] = t_cpu * (n / ns) ** 3
 res["kernel_matrix_build_e2e_s"] = t_k
+# fused route (MarginalLikelihoodEvaluator.logLikelihood, MarginalLikelihoodEvaluator.scala:33-45): X in, (logZ, gradient) out; K, L
+# and the site parameters never cross PCIe
+thg = th.copy(); thg[-1] = 0.1
+kfg = gp.GaussianRbfKernel(gp.GaussianRbfParams(thg[0], thg[1:-1], thg[-1]))
+ev = gp.MarginalLikelihoodEvaluator(gp.AvgBasedStopCriterion(0.01), kfg)
+ev.logLikelihood(X, t, thg)
+t0 = time.perf_counter(); lz, gr = ev.logLikelihood(X, t, thg); dt = time.perf_counter() - t0
+res["fused_logZ_and_gradient"] = {"sweeps": ev.sweeps, "seconds": dt, "s_per_sweep": dt / ev.sweeps, "logZ": lz, "grad_inf_norm": float(np.abs(gr).max())}
 print(json.dumps({"config": f"C3: EP classification n={n}, D=4", **res}))
