@@ -464,6 +464,30 @@ class DistributedGp:
                         L[i * nb:(i + 1) * nb, j * nb:(j + 1) * nb] = part[li * nb:(li + 1) * nb, lj * nb:(lj + 1) * nb]
         return np.tril(L)[:self.n, :self.n]
 
+    def predict_mean(self, Xs, alpha) -> np.ndarray:
+        """Posterior mean K(X*, X) alpha (GpPredictor.scala:53-54) for the fitted training set; block column j of K(X*, X) is
+        generated and contracted on rank j mod world, one all-reduce of m doubles at the end.  (The predictive variance needs a
+        distributed multi-right-hand-side forward solve on the block-cyclic factor and is not built.)"""
+        torch, ops, nb, n, npad = self.torch, self.ops, self.nb, self.n, self.npad
+        Xs = np.atleast_2d(np.asarray(Xs, dtype=np.float64))
+        m, D = Xs.shape
+        if D != self.X.shape[1]:
+            raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, "requirement failed: test point dimension")
+        with ops.run():
+            Xp = np.zeros((npad, D)); Xp[:n] = self.X
+            Xd = Mat(ops.upload(np.asfortranarray(Xp).T), 0, npad)
+            Xsd = Mat(ops.upload(np.asfortranarray(Xs).T), 0, m)
+            ap = np.zeros(npad); ap[:n] = alpha
+            a = ops.upload(ap)
+            Kb = Mat(ops.alloc(m * nb), 0, m)
+            out = ops.alloc(m, zero=True)
+            for j in range(self.rank, self.nt, self.world):
+                ops.cov_cross(Xsd, m, Xd.at(j * nb, 0), nb, D, self.theta, Kb)        # K(X*, X_j): m x nb, no noise
+                ops.gemv(False, m, nb, 1.0, Kb, Vec(a, j * nb), 1.0, Vec(out, 0))
+            self._allreduce(out)
+            ops.synchronize()
+            return out.cpu().numpy().copy()
+
     def residual(self, y, alpha) -> float:
         """||K alpha - y||_2 / ||y||_2 with K regenerated block column by block column (rank r takes columns == r mod world)."""
         torch, ops, nb, n, npad = self.torch, self.ops, self.nb, self.n, self.npad

@@ -135,7 +135,8 @@ def _worker(rank, world, port, grid, n, nb, q):
     fit = solver.fit(X, y, theta)
     L = solver.gather_factor()
     res = solver.residual(y, fit.alphaVec)
-    q.put((rank, fit.logLikelihood, fit.alphaVec, L, res, solver.launch_gemm))
+    pm = solver.predict_mean(X[:9] + 0.01, fit.alphaVec)
+    q.put((rank, fit.logLikelihood, fit.alphaVec, L, res, solver.launch_gemm, pm))
     dist.destroy_process_group()
 
 
@@ -158,7 +159,9 @@ def test_distributed_fit_matches_oracle_on_gloo(world, grid, n, nb):
     L_o, alpha_o = orc.fast_precompute(X, y, theta)
     ll_o = orc.fast_loglik(alpha_o, L_o, y)
     total_gemms = 0
-    for rank, ll, alpha, L, res, ngemm in out:
+    mean_o = orc.fast_build_kernel_matrix(X[:9] + 0.01, np.r_[theta[:-1], 0.0], X) @ alpha_o
+    for rank, ll, alpha, L, res, ngemm, pm in out:
+        assert np.allclose(pm, mean_o, rtol=1e-8, atol=1e-9 * np.abs(mean_o).max())       # posterior mean, replicated
         assert abs(ll - ll_o) <= 1e-9 * abs(ll_o)
         assert np.allclose(alpha, alpha_o, rtol=1e-8, atol=1e-9 * np.abs(alpha_o).max())   # replicated on every rank
         assert res < 1e-10

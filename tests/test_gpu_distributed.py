@@ -31,6 +31,9 @@ def test_single_gpu_block_cholesky_matches_oracle(n, nb, sigma):
     assert np.linalg.norm(L - L_o) <= 1e-9 * np.linalg.norm(L_o)
     if sigma is None:
         assert solver.residual(y, fit.alphaVec) < 1e-10
+    Xs = X[:13] * 0.95 + 0.02
+    mean_o = orc.fast_build_kernel_matrix(Xs, theta, X) @ alpha_o                 # the cross-covariance never carries noise
+    assert np.allclose(solver.predict_mean(Xs, fit.alphaVec), mean_o, rtol=1e-9, atol=1e-9 * np.abs(mean_o).max())
 
 
 def test_not_positive_definite_is_reported_with_its_minor():
