@@ -488,6 +488,74 @@ class DistributedGp:
             ops.synchronize()
             return out.cpu().numpy().copy()
 
+    def predict(self, Xs, alpha):
+        """computePosterior for the large GP (GpPredictor.scala:45-58): mean = K* alpha and the full m x m covariance
+        sigma = K** - V^t V with V = L^-1 K*^t (its diagonal includes noiseVar^2, MatrixUtils.scala:63).  V^t is kept replicated
+        (m x n, stored per process row like the panels) and swept block column by block column: the owners re-broadcast the
+        panel of L, every rank applies V_k^t = B_k^t L_kk^-t and B_i^t -= V_k^t L_ik^t (DMMA GEMMs), then sigma -= V^t V."""
+        torch, ops, nb, n, npad, nt, g = self.torch, self.ops, self.nb, self.n, self.npad, self.nt, self.grid
+        Xs = np.atleast_2d(np.asarray(Xs, dtype=np.float64))
+        m, D = Xs.shape
+        if D != self.X.shape[1]:
+            raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, "requirement failed: test point dimension")
+        M = (m + 127) // 128 * 128
+        mean = self.predict_mean(Xs, alpha)
+        A = self.A
+        with ops.run():
+            Xsp = np.zeros((M, D)); Xsp[:m] = Xs
+            Xsd = Mat(ops.upload(np.asfortranarray(Xsp).T), 0, M)
+            # B^t = K(X*, X) with the training rows in piece-major order (block rows == q mod Pr together); padded rows/cols zero
+            Btq, ncol_q = [], []
+            for q in range(g.Pr):
+                blocks = list(g.row_blocks(q))
+                Xq = np.zeros((max(len(blocks), 1) * nb, D))
+                for l, b in enumerate(blocks):
+                    lo, hi = b * nb, min((b + 1) * nb, n)
+                    if hi > lo:
+                        Xq[l * nb:l * nb + hi - lo] = self.X[lo:hi]
+                cols = len(blocks) * nb
+                buf = Mat(ops.alloc(M * max(cols, 1), zero=True), 0, M)
+                if cols:
+                    ops.cov_cross(Xsd, M, Mat(ops.upload(np.asfortranarray(Xq).T), 0, Xq.shape[0]), cols, D, self.theta, buf)
+                    _view(torch, buf.at(m, 0), M - m, cols).zero_()                       # padded test rows
+                    if blocks and blocks[-1] == nt - 1 and npad > n:                      # padded training rows
+                        pad0 = n - (nt - 1) * nb
+                        _view(torch, buf.at(0, (len(blocks) - 1) * nb + pad0), M, nb - pad0).zero_()
+                Btq.append(buf); ncol_q.append(cols)
+            sigma = Mat(ops.alloc(M * M, zero=True), 0, M)
+            ops.cov_cross(Xsd, M, Xsd, M, D, self.theta, sigma)
+            _view(torch, sigma, M, M)[m:, :].zero_(); _view(torch, sigma, M, M)[:, m:].zero_()
+            ops.add_diag(sigma, m, float(self.theta[-1]) ** 2)                            # sameIndex noise of buildKernelMatrix(k, X*)
+            piece_buf = ops.alloc(max(nt - 1, 1) * nb * nb)
+            Tk = Mat(ops.alloc(M * nb), 0, M)
+            for k in range(nt):
+                oq, oc = k % g.Pr, k % g.Pc
+                first, cnt, off = g.panel_layout(k)
+                works = []
+                if g.pc == oc and cnt[g.pr]:                                              # pack my piece of L's panel k
+                    rows = cnt[g.pr] * nb
+                    src = A.at((first[g.pr] // g.Pr) * nb, (k // g.Pc) * nb)
+                    _view(torch, Mat(piece_buf, off[g.pr] * nb * nb, rows), rows, nb).copy_(_view(torch, src, rows, nb))
+                for q in range(g.Pr):
+                    if cnt[q]:
+                        works.append(self._bcast(piece_buf[off[q] * nb * nb:(off[q] + cnt[q]) * nb * nb], g.rank_of(q, oc)))
+                Bk = Btq[oq].at(0, (k // g.Pr) * nb)
+                ops.gemm_nt(M, nb, nb, 1.0, Bk, Mat(self.Li, k * nb * nb, nb), 0.0, Tk, q_lower_tri=True)   # V_k^t = B_k^t L_kk^-t
+                _view(torch, Bk, M, nb).copy_(_view(torch, Tk, M, nb))
+                self._wait(works)
+                for q in range(g.Pr):
+                    if cnt[q]:
+                        ops.gemm_nt(M, cnt[q] * nb, nb, -1.0, Tk, Mat(piece_buf, off[q] * nb * nb, cnt[q] * nb), 1.0,
+                                    Btq[q].at(0, (first[q] // g.Pr) * nb))                                   # B_i^t -= V_k^t L_ik^t
+                if self.world > 1:
+                    ops.synchronize()      # piece_buf is reused by the next step's broadcasts
+            for q in range(g.Pr):
+                if ncol_q[q]:
+                    ops.gemm_nt(M, M, ncol_q[q], -1.0, Btq[q], Btq[q], 1.0, sigma)                           # sigma -= V^t V
+            ops.synchronize()
+            S = _view(torch, sigma, M, M).cpu().numpy().T[:m, :m].copy()
+        return mean, S
+
     def residual(self, y, alpha) -> float:
         """||K alpha - y||_2 / ||y||_2 with K regenerated block column by block column (rank r takes columns == r mod world)."""
         torch, ops, nb, n, npad = self.torch, self.ops, self.nb, self.n, self.npad

@@ -135,8 +135,8 @@ def _worker(rank, world, port, grid, n, nb, q):
     fit = solver.fit(X, y, theta)
     L = solver.gather_factor()
     res = solver.residual(y, fit.alphaVec)
-    pm = solver.predict_mean(X[:9] + 0.01, fit.alphaVec)
-    q.put((rank, fit.logLikelihood, fit.alphaVec, L, res, solver.launch_gemm, pm))
+    pm, ps = solver.predict(X[:9] + 0.01, fit.alphaVec)
+    q.put((rank, fit.logLikelihood, fit.alphaVec, L, res, solver.launch_gemm, pm, ps))
     dist.destroy_process_group()
 
 
@@ -160,7 +160,9 @@ def test_distributed_fit_matches_oracle_on_gloo(world, grid, n, nb):
     ll_o = orc.fast_loglik(alpha_o, L_o, y)
     total_gemms = 0
     mean_o = orc.fast_build_kernel_matrix(X[:9] + 0.01, np.r_[theta[:-1], 0.0], X) @ alpha_o
-    for rank, ll, alpha, L, res, ngemm, pm in out:
+    _, S_o, _ = orc.fast_compute_posterior(X, X[:9] + 0.01, L_o, alpha_o, theta)
+    for rank, ll, alpha, L, res, ngemm, pm, ps in out:
+        assert np.allclose(ps, S_o, rtol=1e-7, atol=1e-9 * np.abs(S_o).max())             # full predictive covariance, replicated
         assert np.allclose(pm, mean_o, rtol=1e-8, atol=1e-9 * np.abs(mean_o).max())       # posterior mean, replicated
         assert abs(ll - ll_o) <= 1e-9 * abs(ll_o)
         assert np.allclose(alpha, alpha_o, rtol=1e-8, atol=1e-9 * np.abs(alpha_o).max())   # replicated on every rank

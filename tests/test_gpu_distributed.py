@@ -34,6 +34,11 @@ def test_single_gpu_block_cholesky_matches_oracle(n, nb, sigma):
     Xs = X[:13] * 0.95 + 0.02
     mean_o = orc.fast_build_kernel_matrix(Xs, theta, X) @ alpha_o                 # the cross-covariance never carries noise
     assert np.allclose(solver.predict_mean(Xs, fit.alphaVec), mean_o, rtol=1e-9, atol=1e-9 * np.abs(mean_o).max())
+    if sigma is None:                                                                # computePosterior carries no sigmaNoise
+        pm, ps = solver.predict(Xs, fit.alphaVec)
+        _, S_o, _ = orc.fast_compute_posterior(X, Xs, L_o, alpha_o, theta)
+        assert np.allclose(pm, mean_o, rtol=1e-9, atol=1e-9 * np.abs(mean_o).max())
+        assert np.allclose(ps, S_o, rtol=1e-8, atol=1e-9 * np.abs(S_o).max())
 
 
 def test_not_positive_definite_is_reported_with_its_minor():
