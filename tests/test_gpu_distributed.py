@@ -65,11 +65,12 @@ def test_two_gpus_nccl_matches_single_gpu():
     for nproc, grid in ((1, "1x1"), (2, "2x1"), (2, "1x2")):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
                "--master-port", "29731", os.path.join(ROOT, "tools", "bench_c5.py"), "--size", "5000", "--nb", "256", "--grid", grid,
-               "--reps", "1"]
+               "--reps", "1", "--predict", "21"]
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
         assert r.returncode == 0, r.stderr[-2000:]
         outs[grid] = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
         assert outs[grid]["residual_Kalpha_minus_y_over_y"] < 1e-10
+        assert max(outs[grid]["predict_rel_diff_vs_single_handle"]) < 1e-8      # mean and full covariance over NCCL
     for grid in ("2x1", "1x2"):
         assert abs(outs[grid]["ll"] - outs["1x1"]["ll"]) <= 1e-11 * abs(outs["1x1"]["ll"])
 

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--nb", type=int, default=1024)
     ap.add_argument("--grid", type=str, default="")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--predict", type=int, default=0, help="also run DistributedGp.predict at this many test rows and compare with the single-handle path on rank 0")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -49,6 +50,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         times.append(float(t.item()))
     res = solver.residual(y, fit.alphaVec)
+    pred_diff = None
+    if a.predict > 0:
+        Xs = X[:a.predict] * 0.97 + 0.01
+        pm, ps = solver.predict(Xs, fit.alphaVec)
+        if rank == 0:
+            import gp_algos_b200 as gp
+            model = gp.GpPredictor(gp.GaussianRbfKernel(gp.GaussianRbfParams(theta[0], theta[1:-1], theta[-1]))).fit(X, None, y, theta)
+            dist1, _ = model.computePosterior(Xs, full_cov=True, want_v=False)
+            model.close()
+            pred_diff = [float(np.abs(pm - dist1.mean).max() / np.abs(dist1.mean).max()),
+                         float(np.abs(ps - dist1.sigma).max() / np.abs(dist1.sigma).max())]
     if rank == 0:
         best = min(times)
         print(json.dumps({"config": f"C5: n={a.n}, D=8, K build + block-cyclic Cholesky + alpha", "n_gpus": world,
@@ -56,7 +68,8 @@ def main():
                           "potrf_tflops_total": float(a.n) ** 3 / 3 / best * 1e-12,
                           "potrf_tflops_per_gpu": float(a.n) ** 3 / 3 / best * 1e-12 / world,
                           "ll": fit.logLikelihood, "residual_Kalpha_minus_y_over_y": res,
-                          "gemm_launches_rank0": solver.launch_gemm // a.reps}), flush=True)
+                          "gemm_launches_rank0": solver.launch_gemm // a.reps,
+                          "predict_rel_diff_vs_single_handle": pred_diff}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
