@@ -89,9 +89,8 @@ class GPOptimizer:
             raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, "requirement failed: Params m and c needs to be greater or equal 1")
         pointSet = self.prepareGrid(ranges)
         evaluated = self.evaluateGridPoints(pointSet, func)
-        if params.optimizeHpOnInitGrid:
-            raise NotImplementedError("obtainOptimalHyperParams (GpPredictor.scala:126-142) stays with the caller's optimiser")
-        hp = self.hyperParams
+        hp = (self.gpPredictor.obtainOptimalHyperParams(pointSet, self.noise, evaluated, True)     # GPOptimizer.scala:42-46
+              if params.optimizeHpOnInitGrid else self.hyperParams)
         for _ in range(m):                                                            # GPOptimizer.scala:48-77
             model = self.gpPredictor.fit(pointSet, self.noise, evaluated, hp)         # preComputeComponents, resident
             try:
