@@ -142,8 +142,7 @@ def run_gpk(args):
     import torch
     import ctypes as C
     import gp_algos_b200 as gp
-    from gp_algos_b200 import _lib
-    from oracle import gp_oracle as orc  # cpu_baseline leg + workload generator only
+    from gp_algos_b200 import _lib, synthetic   # oracle/ is imported by the cpu_baseline / --impl reference legs only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -156,7 +155,7 @@ def run_gpk(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.n
-    X, y, theta0 = orc.make_c2(n=n, D=DIM)
+    X, y, theta0 = synthetic.make_c2(n=n, D=DIM)
     # each rank = one MLE restart: same data, its own hyper-parameter point
     rng = np.random.default_rng(100 + rank)
     theta = theta0.copy()

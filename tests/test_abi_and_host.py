@@ -132,3 +132,31 @@ def test_obtain_optimal_hyper_params_without_noise_throws_like_the_reference():
     X = np.random.default_rng(0).uniform(size=(10, 2)); y = X[:, 0]
     with pytest.raises(ValueError, match="does not equal to 4"):
         pred.obtainOptimalHyperParams(X, None, y, optimizeNoise=False)
+
+
+def test_synthetic_workloads_match_the_oracles_generators():
+    """bench.py / tools build their inputs with gp_algos_b200.synthetic (so the measured paths never import oracle/); the tests
+    use the oracle's generators.  Both must produce the same SURVEY.md 8(d) workloads bit for bit."""
+    from gp_algos_b200 import synthetic
+    from oracle import gp_oracle as orc
+    for a, b in ((synthetic.make_c1(50, 7), orc.make_c1(50, 7)), (synthetic.make_c2(64, 8), orc.make_c2(64, 8)),
+                 (synthetic.make_c2(40, 8, seed=5), orc.make_c2(40, 8, seed=5)), (synthetic.make_c3(33, 4), orc.make_c3(33, 4)),
+                 (synthetic.make_c4_problem(3, n=20), orc.make_c4_problem(3, n=20))):
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_product_and_tools_never_import_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for sub in ("gp_algos_b200", "tools"):
+        for fn in sorted(os.listdir(os.path.join(root, sub))):
+            if fn.endswith(".py"):
+                src = open(os.path.join(root, sub, fn)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M):
+                    offenders.append(f"{sub}/{fn}")
+    assert offenders == []
+    # bench.py may only reach oracle/ from its CPU legs (cpu_baseline and --impl reference)
+    bench = open(os.path.join(root, "bench.py")).read()
+    gpu_arm = bench[bench.index("def run_gpk"):]
+    head, tail = gpu_arm.split("t_cpu = cpu_eval_time", 1)
+    assert "oracle" not in head.replace("oracle/ is imported by the cpu_baseline", "").replace("oracle LAPACK", "")

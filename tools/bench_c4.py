@@ -7,7 +7,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from gp_algos_b200 import _lib, batched
-from oracle import gp_oracle as orc
+from gp_algos_b200 import synthetic
 
 B, N, D, M = int(os.environ.get("C4_B", 512)), 1024, 8, 17
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -17,7 +17,7 @@ if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 lo, hi = batched.shard_bounds(B, rank, world)
-probs = [orc.make_c4_problem(b) for b in range(lo, hi)]
+probs = [synthetic.make_c4_problem(b) for b in range(lo, hi)]
 X = np.stack([p[0] for p in probs]); ys = np.stack([p[1] for p in probs]); Xs = np.stack([p[2] for p in probs]); th = np.stack([p[3] for p in probs])
 ts = torch.cuda.Stream(priority=-1); torch.cuda.set_stream(ts)
 h = _lib.Handle(local, ts.cuda_stream)
@@ -49,10 +49,12 @@ vals = torch.tensor([ms * 1e-3, t_e2e, t_pred], dtype=torch.float64, device="cud
 if dist is not None: dist.all_reduce(vals, op=dist.ReduceOp.MAX)
 if rank == 0:
     tm, te, tp = [float(v) for v in vals.tolist()]
-    # spot parity on one problem
-    llo, go = orc.fast_loglik_with_derivs(X[0], ys[0], th[0])
+    # cross-check: problem 0 through the single-problem entry point (parity with the oracle is tests/test_gpu_batched.py's job)
+    import gp_algos_b200 as gp
+    llo, go = gp.GpPredictor(gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0][0], th[0][1:-1], th[0][-1])), h).logLikelihoodWithDerivatives(
+        gp.PredictionTrainingInput(X[0], None, ys[0]), th[0], 10)
     print(json.dumps({"config": f"C4: {B} independent GPs, n={N}, D={D}, m={M}; {world} GPU(s), {hi - lo} problems on rank 0, no collective",
                       "nll_grad_problems_per_s": B / tm, "nll_grad_ms_per_batch": tm * 1e3, "nll_grad_eff_tflops": B * float(N) ** 3 / tm * 1e-12,
                       "nll_grad_e2e_problems_per_s": B / te, "fit_predict_e2e_problems_per_s": B / tp, "launches_per_batch": int(launches),
-                      "n_gpus": world, "parity_ll_rel": abs(ll[0] - llo) / abs(llo)}))
+                      "n_gpus": world, "batched_vs_single_ll_rel": abs(ll[0] - llo) / abs(llo)}))
 if dist is not None: dist.destroy_process_group()

@@ -13,16 +13,6 @@ import torch
 import torch.distributed as dist
 
 
-def synth(n, D=8, seed=5):
-    """as C2 with seed 5 (same generator as oracle.make_c2, restated so the tool has no oracle import)."""
-    rng = np.random.default_rng(seed)
-    X = rng.uniform(0.0, 1.0, size=(n, D))
-    w = rng.standard_normal(D)
-    y = np.sin(X @ w) + 0.1 * rng.standard_normal(n)
-    theta = np.concatenate([[1.0], np.full(D, 0.7), [0.1]])
-    return X, y, theta
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", dest="n", type=int, default=65536)
@@ -40,7 +30,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gp_algos_b200.distributed import DistributedGp, choose_grid
     grid = tuple(int(v) for v in a.grid.split("x")) if a.grid else choose_grid(world)
-    X, y, theta = synth(a.n)
+    from gp_algos_b200 import synthetic
+    X, y, theta = synthetic.make_c2(n=a.n, D=8, seed=5)     # as C2 with seed 5
     solver = DistributedGp(grid=grid, nb=a.nb, device=local)
     times = []
     for _ in range(a.reps):

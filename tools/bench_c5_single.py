@@ -4,10 +4,10 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import gp_algos_b200 as gp
-from oracle import gp_oracle as orc
+from gp_algos_b200 import synthetic
 
 n = int(os.environ.get("C5_N", 65536))
-X, y, th = orc.make_c2(n=n, D=8, seed=5)
+X, y, th = synthetic.make_c2(n=n, D=8, seed=5)
 kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
 pred = gp.GpPredictor(kf)
 t0 = time.perf_counter(); fitted = pred.fit(X, None, y, th); t_first = time.perf_counter() - t0

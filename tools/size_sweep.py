@@ -2,11 +2,11 @@ import sys, os, time, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from gp_algos_b200 import _lib
-from oracle import gp_oracle as orc
+from gp_algos_b200 import synthetic
 ts = torch.cuda.Stream(priority=-1); torch.cuda.set_stream(ts)
 h = _lib.Handle(0, ts.cuda_stream)
 for n in (128, 256, 512, 1024, 2048, 4096, 8192):
-    X, y, th = orc.make_c2(n=n)
+    X, y, th = synthetic.make_c2(n=n)
     dX = torch.from_numpy(np.asfortranarray(X).T.copy()).cuda(); dy = torch.from_numpy(y).cuda()
     out = torch.zeros(11, dtype=torch.float64, device="cuda"); info = torch.zeros(1, dtype=torch.int32, device="cuda")
     thc = np.ascontiguousarray(th)
