@@ -225,3 +225,27 @@ def test_maximum_feature_dimension_and_beyond():
     X65 = rng.uniform(size=(50, 65)); th65 = orc.pack_theta(1.0, np.ones(65), 0.1)
     with pytest.raises(ValueError):
         _pred(th65).logLikelihoodWithDerivatives(gp.PredictionTrainingInput(X65, None, y[:50]), th65, 67)
+
+
+def test_randomised_shapes_and_hyperparameters_sweep():
+    """40 seeded random problems (n in 1..700 across the 128-padding boundaries, D in 1..12, random theta and Option sigmaNoise):
+    objective, gradient and predictive moments against the LAPACK-backed oracle."""
+    rng = np.random.default_rng(20240)
+    for trial in range(40):
+        n = int(rng.choice([1, 2, 3, 127, 128, 129, 255, 256, 257, 383, 385, 511, 513])) if trial % 2 == 0 else int(rng.integers(4, 700))
+        D = int(rng.integers(1, 13))
+        m = int(rng.integers(1, 20))
+        X = rng.uniform(-1.0, 1.0, size=(n, D)) * rng.uniform(0.5, 3.0)
+        y = np.sin(X @ rng.standard_normal(D)) + 0.2 * rng.standard_normal(n)
+        th = orc.pack_theta(10 ** rng.uniform(-0.3, 0.5), 10 ** rng.uniform(-0.3, 0.6, size=D), 10 ** rng.uniform(-1.0, -0.3))
+        s = None if rng.uniform() < 0.5 else float(10 ** rng.uniform(-2, -0.5))
+        p = _pred(th)
+        ll, g = p.logLikelihoodWithDerivatives(gp.PredictionTrainingInput(X, s, y), th, D + 2)
+        llo, go = orc.fast_loglik_with_derivs(X, y, th, s)
+        assert abs(ll - llo) <= RTOL * max(abs(llo), 1.0), (trial, n, D, ll, llo)
+        assert_grad(g, go)
+        Xs = rng.uniform(-1.0, 1.0, size=(m, D))
+        dist, ll2 = p.predict(gp.PredictionInput(X, Xs, s, y), th)
+        mo, So, _ = orc.fast_predict(X, y, Xs, th, s)
+        assert_rel(dist.mean, mo, atol=RTOL * max(np.abs(mo).max(), 1e-3))
+        assert_rel(np.diag(dist.sigma), np.diag(So), rtol=1e-8)      # cond(K) reaches ~1e6 in this sweep
