@@ -64,6 +64,7 @@ def load():
         lib.gpk_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
         lib.gpk_destroy.argtypes = [C.c_void_p]
         lib.gpk_synchronize.argtypes = [C.c_void_p]
+        lib.gpk_set_graph_mode.argtypes = [C.c_void_p, C.c_int]
         vp, ci, cd = C.c_void_p, C.c_int, C.c_double
         lib.gpk_cov_se_ard.argtypes = [vp, vp, ci, ci, _i64, vp, vp, _i64]
         lib.gpk_cov_se_ard_dev.argtypes = [vp, vp, ci, ci, _i64, vp, vp, _i64]
@@ -81,6 +82,8 @@ def load():
         lib.gpk_gp_model_from_factor.argtypes = [vp, vp, ci, ci, _i64, vp, _i64, vp, vp, C.POINTER(vp)]
         lib.gpk_gp_model_destroy.argtypes = [vp, vp]
         lib.gpk_gp_model_get_alpha.argtypes = [vp, vp, vp]
+        lib.gpk_gp_model_append.argtypes = [vp, vp, vp, cd, ci, cd, vp]
+        lib.gpk_gp_model_size.argtypes = [vp, vp]
         lib.gpk_gp_model_predict.argtypes = [vp, vp, vp, ci, _i64, ci, vp, vp, _i64, vp, _i64]
         lib.gpk_gp_models_mean.argtypes = [vp, vp, ci, vp, ci, _i64, vp]
         lib.gpk_gp_model_ucb.argtypes = [vp, vp, vp, ci, _i64, cd, vp, vp, _i64, vp, vp]
@@ -131,6 +134,10 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self.lib.gpk_launch_count(self._h))
+
+    def set_graph_mode(self, on: bool):
+        """CUDA-graph replay of repeated logLikelihoodWithDerivatives calls (include/gpk.h); on by default."""
+        self.check(self.lib.gpk_set_graph_mode(self._h, 1 if on else 0))
 
     def synchronize(self):
         self.check(self.lib.gpk_synchronize(self._h))

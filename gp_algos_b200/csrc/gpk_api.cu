@@ -23,10 +23,15 @@ int gpk_set_error(gpk_handle h, int status, const char* fmt, ...) {
 
 void* gpk_arena(gpk_handle h, int which, size_t bytes) {
     if (bytes <= h->arena_bytes[which] && h->arena[which]) return h->arena[which];
+    if (h->cap) {  // stream capture in progress: allocation would synchronise; the capturing caller falls back to eager launches
+        gpk_set_error(h, GPK_ENOMEM, "arena %d would have to grow during graph capture", which);
+        return nullptr;
+    }
     if (h->arena[which]) {
         cudaStreamSynchronize(h->stream);
         for (int i = 0; i < GPK_NSIDE; ++i) cudaStreamSynchronize(h->side[i]);
         for (int i = 0; i < GPK_NPIPE; ++i) cudaStreamSynchronize(h->pipe[i]);
+        for (int i = 0; i < GPK_NGROUP - 1; ++i) cudaStreamSynchronize(h->grp[i]);
         cudaFree(h->arena[which]);
         h->arena[which] = nullptr;
         h->arena_bytes[which] = 0;
@@ -40,6 +45,7 @@ void* gpk_arena(gpk_handle h, int which, size_t bytes) {
     }
     h->arena[which] = p;
     h->arena_bytes[which] = bytes;
+    h->arena_epoch++;
     return p;
 }
 
@@ -107,10 +113,16 @@ int gpk_create(gpk_handle* out, int device, void* stream) {
     cudaStreamGetPriority(h->stream, &mainprio);
     // numerically lower = more urgent; [greatest, least] is e.g. [-5, 0]
     const int sideprio = (mainprio < least && least - 1 >= greatest) ? least - 1 : least;
+    h->prio_main = mainprio; h->prio_side = sideprio; h->prio_pipe = least;
+    const char* gm = getenv("GPK_GRAPH");
+    const char* tr = getenv("GPK_TRACE");
+    h->graph_mode = (tr && atoi(tr) > 0) ? 0 : (gm ? atoi(gm) : 1);   // the trace timeline needs eager launches
     for (int i = 0; i < GPK_NSIDE; ++i)
         if (cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, sideprio) != cudaSuccess) { delete h; return GPK_ECUDA; }
     for (int i = 0; i < GPK_NPIPE; ++i)
         if (cudaStreamCreateWithPriority(&h->pipe[i], cudaStreamNonBlocking, least) != cudaSuccess) { delete h; return GPK_ECUDA; }
+    for (int i = 0; i < GPK_NGROUP - 1; ++i)
+        if (cudaStreamCreateWithPriority(&h->grp[i], cudaStreamNonBlocking, mainprio) != cudaSuccess) { delete h; return GPK_ECUDA; }
     for (int i = 0; i < GPK_NEVENTS; ++i)
         if (cudaEventCreateWithFlags(&h->evpool[i], cudaEventDisableTiming) != cudaSuccess) { delete h; return GPK_ECUDA; }
     *out = h;
@@ -121,10 +133,13 @@ int gpk_destroy(gpk_handle h) {
     if (!h) return GPK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    gpk_eval_graph_drop(h);
     for (int i = 0; i < GPK_NSIDE; ++i)
         if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
     for (int i = 0; i < GPK_NPIPE; ++i)
         if (h->pipe[i]) { cudaStreamSynchronize(h->pipe[i]); cudaStreamDestroy(h->pipe[i]); }
+    for (int i = 0; i < GPK_NGROUP - 1; ++i)
+        if (h->grp[i]) { cudaStreamSynchronize(h->grp[i]); cudaStreamDestroy(h->grp[i]); }
     for (int i = 0; i < GPK_NARENA; ++i)
         if (h->arena[i]) cudaFree(h->arena[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -140,6 +155,12 @@ int gpk_destroy(gpk_handle h) {
 const char* gpk_last_error(gpk_handle h) { return h ? h->err : "null handle"; }
 int gpk_last_info(gpk_handle h) { return h ? h->last_info : 0; }
 int64_t gpk_launch_count(gpk_handle h) { return h ? h->launches : 0; }
+int gpk_set_graph_mode(gpk_handle h, int on) {
+    if (!h) return GPK_EINVAL;
+    h->graph_mode = on ? 1 : 0;
+    if (!on) { cudaStreamSynchronize(h->stream); gpk_eval_graph_drop(h); }
+    return GPK_OK;
+}
 
 int gpk_synchronize(gpk_handle h) {
     GPK_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -34,6 +34,7 @@ struct Ctx {
     int batch;
     int64_t sM;            // matrix stride between problems (N*N)
     int64_t sT;            // scratch stride between problems
+    int side_base;         // first side stream of this batch group
 };
 
 struct StreamSwap {  // run the enclosed launches on another stream of the same handle
@@ -56,6 +57,12 @@ int pipe_nb() {      // block-column width of the pipelined driver
 int pipe_min() {     // smallest padded N that takes the pipelined driver (0 disables it)
     static int v = -1;
     if (v < 0) { const char* e = getenv("GPK_PIPE_MIN"); v = e ? atoi(e) : 4096; }
+    return v;
+}
+
+int batch_group_min() {   // smallest batch that is split into GPK_NGROUP concurrent groups (0 or less: never)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPK_GROUP_MIN"); v = e ? atoi(e) : 8; if (v <= 0) v = 1 << 30; }
     return v;
 }
 
@@ -112,7 +119,7 @@ int potrf_inv_rec(const Ctx& c, double* A, double* Li, double* T, int n, int col
     const bool fork = n >= side_min();
     cudaEvent_t ev_done = nullptr;
     if (fork) {
-        cudaStream_t side = h->side[depth % GPK_NSIDE];
+        cudaStream_t side = h->side[(c.side_base + depth) % GPK_NSIDE];
         cudaEvent_t ev_l21 = h->evpool[h->ev_next++ % GPK_NEVENTS];
         ev_done = h->evpool[h->ev_next++ % GPK_NEVENTS];
         GPK_CUDA(h, cudaEventRecord(ev_l21, h->stream));
@@ -234,7 +241,7 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     const int nt = (N + nbk - 1) / nbk;
     auto bs = [&](int k) { return k * nbk < N ? k * nbk : N; };
     GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
-    Ctx c{h, N, N, keep_L, info_dev, 1, (int64_t)N * N, 0};
+    Ctx c{h, N, N, keep_L, info_dev, 1, (int64_t)N * N, 0, 0};
     double* Tdiag = T;
     double* Trow = T + rec_scratch_doubles(nbk);
     cudaStream_t M = h->stream, S = h->pipe[0], S2 = h->pipe[1], S3 = h->pipe[2];
@@ -365,8 +372,40 @@ bool gpk_use_pipelined(int N, int batch) { return batch == 1 && pipe_min() > 0 &
 int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int* info_dev, int batch) {
     if (gpk_use_pipelined(N, batch)) return gpk_potrf_inv_pipelined(h, A, Li, nullptr, T, N, keep_L, info_dev, nullptr);
     GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int) * (size_t)batch, h->stream));
-    Ctx c{h, N, N, keep_L, info_dev, batch, (int64_t)N * N, (int64_t)gpk_chol_scratch_doubles(N)};
-    return potrf_inv_rec(c, A, Li, T, N, 0, 0);
+    const int64_t sM = (int64_t)N * N, sT = (int64_t)gpk_chol_scratch_doubles(N);
+    const int groups = (batch >= batch_group_min()) ? GPK_NGROUP : 1;
+    if (groups == 1) {
+        Ctx c{h, N, N, keep_L, info_dev, batch, sM, sT, 0};
+        return potrf_inv_rec(c, A, Li, T, N, 0, 0);
+    }
+    // Batch groups: the problems are independent, so the batch is cut in two halves that walk the recursion on two streams.
+    // The base-case launches (one CTA per problem, latency-bound, ~40 us each, 8 per factorisation at n = 1024) and the
+    // partial last waves of the small GEMMs of one half are filled by the other half's launches.
+    cudaEvent_t ev0 = next_event(h);
+    GPK_CUDA(h, cudaEventRecord(ev0, h->stream));
+    const int per = (batch + groups - 1) / groups;
+    int rc = GPK_OK;
+    cudaEvent_t done[GPK_NGROUP];
+    for (int g = groups - 1; g >= 0 && !rc; --g) {       // the handle's own stream last: its launches need no join
+        const int b0 = g * per, cnt = (batch - b0 < per) ? batch - b0 : per;
+        done[g] = nullptr;
+        if (cnt <= 0) continue;
+        cudaStream_t st = g == 0 ? h->stream : h->grp[g - 1];
+        if (g > 0) GPK_CUDA(h, cudaStreamWaitEvent(st, ev0, 0));
+        {
+            StreamSwap sw(h, st);
+            Ctx c{h, N, N, keep_L, info_dev + b0, cnt, sM, sT, 4 * g};
+            rc = potrf_inv_rec(c, A + b0 * sM, Li + b0 * sM, T + b0 * sT, N, 0, 0);
+        }
+        if (g > 0 && !rc) {
+            done[g] = next_event(h);
+            GPK_CUDA(h, cudaEventRecord(done[g], st));
+        }
+    }
+    if (rc) return rc;
+    for (int g = 1; g < groups; ++g)
+        if (done[g]) GPK_CUDA(h, cudaStreamWaitEvent(h->stream, done[g], 0));
+    return GPK_OK;
 }
 
 int gpk_trtri_lower(gpk_handle h, const double* L, double* Li, double* T, int N) {
@@ -374,7 +413,7 @@ int gpk_trtri_lower(gpk_handle h, const double* L, double* Li, double* T, int N)
     int rc = gpk_base_potrf_trtri(h, const_cast<double*>(L), N, Li, N, h->d_info, 0, 1, N / NB, (int64_t)NB * (N + 1),
                                   (int64_t)NB * (N + 1), 0, NB);
     if (rc) return rc;
-    Ctx c{h, N, N, 0, h->d_info, 1, (int64_t)N * N, (int64_t)gpk_chol_scratch_doubles(N)};
+    Ctx c{h, N, N, 0, h->d_info, 1, (int64_t)N * N, (int64_t)gpk_chol_scratch_doubles(N), 0};
     return trtri_rec(c, L, Li, T, N);
 }
 

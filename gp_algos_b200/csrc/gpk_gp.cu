@@ -10,6 +10,56 @@
 #include <stdlib.h>
 
 #include <new>
+#include <utility>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------------------------
+// CUDA-graph replay of the single-problem evaluation.  One logLikelihoodWithDerivatives call at n = 8192 is ~350 kernel
+// launches plus ~300 event records / waits on 8 streams; an optimiser (GpPredictor.scala:126-142 -> Optimization.scala:30-61)
+// repeats exactly that launch sequence 25-60 times with new hyper-parameters.  The second call with one signature
+// (same device buffers, shape and workspace) is stream-captured, instantiated once and replayed from then on, so a
+// call costs the host two launches -- the throughput no longer depends on how fast (or how contended: 8 ranks on one
+// box) the host thread enqueues.  Hyper-parameters reach the kernels through a ProblemParams record in device memory
+// that a one-thread kernel rewrites in front of every replay, so the graph itself never changes.
+// ------------------------------------------------------------------------------------------------------------------
+struct gpk_capture_log {
+    std::vector<std::pair<cudaGraphNode_t, int>> nodes;   // kernel node, priority of the stream it was launched on
+};
+struct gpk_eval_graph {
+    const double* dX; const double* dy; double* out; int* info;   // signature of the captured call
+    int n, D, nparams; int64_t ldx; unsigned arena_epoch;
+    int calls;               // eager calls seen with this signature
+    int failed;              // capture was refused once: stay eager
+    cudaGraphExec_t exec;    // null until captured
+    int kernels;             // kernel nodes per replay (gpk_launch_count)
+};
+
+void gpk_capture_note(gpk_handle h) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t nd = 0;
+    if (cudaStreamGetCaptureInfo(h->stream, &st, nullptr, nullptr, &deps, &nd) != cudaSuccess) { cudaGetLastError(); return; }
+    if (st != cudaStreamCaptureStatusActive || nd != 1) return;   // right after a launch the stream depends on exactly that node
+    // stream classes: 0 main (the spine), 1 side (forked GEMMs of a recursion node), 2.. the look-ahead driver's bulk streams
+    int cls = 0;
+    for (int i = 0; i < GPK_NSIDE; ++i) if (h->stream == h->side[i]) cls = 1;
+    for (int i = 0; i < GPK_NPIPE; ++i) if (h->stream == h->pipe[i]) cls = 2 + i;
+    int prio = cls == 0 ? h->prio_main : cls == 1 ? h->prio_side : h->prio_pipe;
+    static int over[2 + GPK_NPIPE], have = -1;
+    if (have < 0) {   // GPK_GRAPH_PRIO="main,side,pipe0,pipe1,pipe2" (tuning aid)
+        const char* e = getenv("GPK_GRAPH_PRIO");
+        have = e && sscanf(e, "%d,%d,%d,%d,%d", &over[0], &over[1], &over[2], &over[3], &over[4]) == 5;
+    }
+    if (have) prio = over[cls];
+    h->cap->nodes.emplace_back(deps[0], prio);
+}
+
+void gpk_eval_graph_drop(gpk_handle h) {
+    if (!h || !h->eval_graph) return;
+    if (h->eval_graph->exec) cudaGraphExecDestroy(h->eval_graph->exec);
+    delete h->eval_graph;
+    h->eval_graph = nullptr;
+}
 
 namespace {
 
@@ -90,8 +140,8 @@ int stage_params(gpk_handle h, const double* thetas, int D, int has_s, double s,
 // K -> L^-1 (and L when keep_L), alpha, ll for `B` resident problems.  X, y on the device.
 int fit_core(gpk_handle h, const Work& w, int B, const double* dX, int n, int D, int64_t ldx, int64_t strideX, const double* dy,
              const ProblemParams& pp0, int keep_L, double* Li, double* alpha, double* ll_dev, int64_t ll_stride, int* info_dev,
-             double* Kinv = nullptr, cudaEvent_t* kinv_done = nullptr) {
-    const ProblemParams* ppd = (B > 1) ? w.pp_dev : nullptr;
+             double* Kinv = nullptr, cudaEvent_t* kinv_done = nullptr, bool params_on_device = false) {
+    const ProblemParams* ppd = (B > 1 || params_on_device) ? w.pp_dev : nullptr;
     int rc = gpk_cov_sym_lower_padded(h, dX, n, ldx, pp0.cp, w.A, w.N, B, strideX, ppd);
     if (rc) return rc;
     // Kinv != nullptr: the look-ahead driver also accumulates K^-1 = L^-t L^-1 while it factors (one large problem only)
@@ -107,16 +157,21 @@ int fit_core(gpk_handle h, const Work& w, int B, const double* dX, int n, int D,
     return gpk_loglik(h, w.A, w.N, n, w.ypad, alpha, ll_dev, B, ll_stride);  // GpPredictor.scala:144-149
 }
 
+// params_on_device (B == 1 only): the caller has already written the problem's ProblemParams to w.pp_dev on the handle's
+// stream and *pp_single holds the same record; every kernel reads the device copy (graph replay, see the top of this file).
 int nll_grad_core(gpk_handle h, int B, const double* dX, int n, int D, int64_t ldx, int64_t strideX, const double* dy,
-                  const double* thetas, int has_s, double s, int nparams, double* out_dev, int* info_dev) {
+                  const double* thetas, int has_s, double s, int nparams, double* out_dev, int* info_dev,
+                  const ProblemParams* pp_single = nullptr) {
     Work w;
     int rc = make_work(h, n, D, B, &w);
     if (rc) return rc;
     const int64_t so = nparams + 1;
+    const bool on_dev = pp_single != nullptr;
     for (int b0 = 0; b0 < B; b0 += w.B) {
         const int bc = (B - b0 < w.B) ? B - b0 : w.B;
         ProblemParams pp0;
-        rc = stage_params(h, thetas + (size_t)b0 * (D + 2), D, has_s, s, bc, w.pp_dev, &pp0);
+        if (on_dev) pp0 = *pp_single;
+        else rc = stage_params(h, thetas + (size_t)b0 * (D + 2), D, has_s, s, bc, w.pp_dev, &pp0);
         if (rc) return rc;
         const double* X = dX + b0 * strideX;
         int* info = info_dev ? info_dev + b0 : (B == 1 ? h->d_info : w.info_dev);
@@ -127,7 +182,7 @@ int nll_grad_core(gpk_handle h, int B, const double* dX, int n, int D, int64_t l
         }
         cudaEvent_t kinv_done = nullptr;
         rc = fit_core(h, w, bc, X, n, D, ldx, strideX, dy + (size_t)b0 * n, pp0, 0, w.Li, w.alpha, out_dev + b0 * so, so, info, Kinv,
-                      &kinv_done);
+                      &kinv_done, on_dev);
         if (rc) return rc;
         if (kinv_done) GPK_CUDA(h, cudaStreamWaitEvent(h->stream, kinv_done, 0));   // alpha / ll above overlapped the last K^-1 row
         if (nparams > 0) {
@@ -136,10 +191,86 @@ int nll_grad_core(gpk_handle h, int B, const double* dX, int n, int D, int64_t l
                 if (rc) return rc;
             }
             rc = gpk_grad_trace(h, Kinv ? Kinv : w.A, w.N, X, n, ldx, w.alpha, pp0, nparams, out_dev + b0 * so + 1, w.scratch, bc, strideX,
-                                bc > 1 ? w.pp_dev : nullptr, so);
+                                (bc > 1 || on_dev) ? w.pp_dev : nullptr, so);
             if (rc) return rc;
         }
     }
+    return GPK_OK;
+}
+
+__global__ void store_params_kernel(const ProblemParams pp, ProblemParams* __restrict__ dst) {
+    if (threadIdx.x == 0) *dst = pp;
+}
+
+// The single-problem evaluation through the graph cache (see the top of this file).
+int nll_grad_single(gpk_handle h, const double* dX, int n, int D, int64_t ldx, const double* dy, const double* theta, int has_s,
+                    double s, int nparams, double* out_dev, int* info_dev) {
+    if (!h->graph_mode) return nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev);
+    ProblemParams pp;
+    int rc = gpk_make_problem_params(h, theta, D, has_s, s, &pp);
+    if (rc) return rc;
+    Work w;
+    rc = make_work(h, n, D, 1, &w);     // sizes every arena now, so that the epoch below is final
+    if (rc) return rc;
+    if (nparams > 0 && gpk_use_pipelined(w.N, 1) && !gpk_arena(h, ARENA_KINV, (size_t)w.N * w.N * sizeof(double))) return GPK_ENOMEM;
+    gpk_eval_graph* g = h->eval_graph;
+    if (!g || g->dX != dX || g->dy != dy || g->out != out_dev || g->info != info_dev || g->n != n || g->D != D ||
+        g->nparams != nparams || g->ldx != ldx || g->arena_epoch != h->arena_epoch) {
+        gpk_eval_graph_drop(h);
+        g = new (std::nothrow) gpk_eval_graph();
+        if (!g) return gpk_set_error(h, GPK_ENOMEM, "host allocation failed");
+        memset(g, 0, sizeof(*g));
+        g->dX = dX; g->dy = dy; g->out = out_dev; g->info = info_dev; g->n = n; g->D = D; g->nparams = nparams; g->ldx = ldx;
+        g->arena_epoch = h->arena_epoch;
+        h->eval_graph = g;
+    }
+    store_params_kernel<<<1, 32, 0, h->stream>>>(pp, w.pp_dev);
+    GPK_LAUNCH_CHECK(h);
+    if (g->exec) {
+        GPK_CUDA(h, cudaGraphLaunch(g->exec, h->stream));
+        h->launches += g->kernels;
+        return GPK_OK;
+    }
+    if (g->failed || g->calls++ == 0)   // first call with this signature: eager (it also sizes the workspace and sets kernel attributes)
+        return nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev, &pp);
+    // second call: record the same launch sequence instead of running it
+    gpk_capture_log log;
+    const int64_t l0 = h->launches;
+    GPK_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->cap = &log;
+    rc = nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev, &pp);
+    h->cap = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    const int kernels = (int)(h->launches - l0);
+    h->launches = l0;
+    if (rc == GPK_OK && ce == cudaSuccess && graph) {
+        for (auto& nd : log.nodes) {          // keep the streams' priorities: the look-ahead spine must overtake the bulk updates
+            cudaLaunchAttributeValue v;
+            memset(&v, 0, sizeof(v));
+            v.priority = nd.second;
+            if (cudaGraphKernelNodeSetAttribute(nd.first, cudaLaunchAttributePriority, &v) != cudaSuccess) cudaGetLastError();
+        }
+        // without this flag every node runs at the priority of the stream the graph is launched into
+        ce = cudaGraphInstantiate(&g->exec, graph, cudaGraphInstantiateFlagUseNodePriority);
+    }
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != GPK_OK || ce != cudaSuccess || !g->exec) {
+        cudaGetLastError();
+        g->exec = nullptr;
+        g->failed = 1;
+        if (getenv("GPK_GRAPH_DEBUG")) fprintf(stderr, "[gpk] graph capture refused (rc %d, %s): staying eager\n", rc, cudaGetErrorString(ce));
+        return nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev, &pp);
+    }
+    g->kernels = kernels;
+    if (getenv("GPK_GRAPH_DEBUG")) {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        fprintf(stderr, "[gpk] evaluation captured: %d kernel nodes (%zu with a priority; handle priorities main %d side %d bulk %d, "
+                "device range %d..%d)\n", kernels, log.nodes.size(), h->prio_main, h->prio_side, h->prio_pipe, greatest, least);
+    }
+    GPK_CUDA(h, cudaGraphLaunch(g->exec, h->stream));
+    h->launches += g->kernels;
     return GPK_OK;
 }
 
@@ -150,7 +281,7 @@ int nll_grad_core(gpk_handle h, int B, const double* dX, int n, int D, int64_t l
 //   dvar   = 0 - 2 sum_i G_id u_i,  u = L^-t (L^-1 k*)                     derAfterVarFirst(x,x) = 0; (L^-1 G)^t v = G^t L^-t v
 //   grad   = dmean + dvar * k / (2 sqrt(sigma))
 __global__ void __launch_bounds__(256) ucb_grad_kernel(const double* __restrict__ KsT, const double* __restrict__ U, int N, int n,
-                                                       const double* __restrict__ X, const double* __restrict__ Xs, int ms,
+                                                       const double* __restrict__ X, int ldx, const double* __restrict__ Xs, int ms,
                                                        const double* __restrict__ alpha, const double* __restrict__ colsq,
                                                        const double* __restrict__ mean, CovParams cp, double kparam,
                                                        double* __restrict__ grad, double* __restrict__ ucb, double* __restrict__ var) {
@@ -159,7 +290,7 @@ __global__ void __launch_bounds__(256) ucb_grad_kernel(const double* __restrict_
     const double xd = Xs[c + (int64_t)d * ms], inv = cp.inv_ls2[d];
     const double* ks = KsT + (int64_t)c * N;
     const double* u = U + (int64_t)c * N;
-    const double* xcol = X + (int64_t)d * n;
+    const double* xcol = X + (int64_t)d * ldx;
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) {
         const double g = ((xd - xcol[i]) * inv) * (-ks[i]);
@@ -184,12 +315,61 @@ __global__ void __launch_bounds__(256) ucb_grad_kernel(const double* __restrict_
 
 struct gpk_model_s {
     int n, N, D;
-    double* X;      // n x D, ld n
+    int ldx;        // rows allocated for X (>= n; == N so that gpk_gp_model_append has room)
+    double* X;      // n x D, ld ldx
     double* Li;     // N x N
     double* alpha;  // N
     double theta[GPK_MAX_D + 2];
     ProblemParams pp;
 };
+
+namespace {
+
+int upload_model_x(gpk_handle h, gpk_model m, const double* X, int64_t ldx) {   // host n x D (ld ldx) -> device (ld m->ldx)
+    GPK_CUDA(h, cudaMemcpy2DAsync(m->X, (size_t)m->ldx * sizeof(double), X, (size_t)ldx * sizeof(double), (size_t)m->n * sizeof(double),
+                                  (size_t)m->D, cudaMemcpyHostToDevice, h->stream));
+    return GPK_OK;
+}
+
+// Bordered update of a resident model by one training point (gpk_gp_model_append).  With k = k(X, x), l = L^-1 k,
+// d^2 = k(x,x) - l.l, w = L^-t l = K^-1 k and zeta = (y - k.alpha) / d   (l . L^-1 y_old = k . alpha):
+//   L_new^-1 = [ L^-1 0 ; -w^t/d  1/d ],   alpha_new = [ alpha - w zeta/d ; zeta/d ].
+// dots = { l.l, k.alpha }.  A non-positive d^2 sets *info = n+1 (the failing leading minor) and changes nothing.
+__global__ void __launch_bounds__(256) model_append_kernel(double* __restrict__ Li, int N, int n, double* __restrict__ alpha,
+                                                           double* __restrict__ X, int ldx, int D, const double* __restrict__ xnew,
+                                                           const double* __restrict__ w, const double* __restrict__ dots, double kss,
+                                                           double ynew, int* __restrict__ info, double* __restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const double d2 = kss - dots[0];
+    if (!(d2 > 0.0)) {
+        if (i == 0) *info = n + 1;
+        return;
+    }
+    const double d = sqrt(d2), zeta = (ynew - dots[1]) / d;
+    if (i < n) {
+        const double u = -w[i] / d;
+        Li[n + (int64_t)i * N] = u;
+        alpha[i] += u * zeta;
+    } else if (i == n) {
+        Li[n + (int64_t)n * N] = 1.0 / d;
+        alpha[n] = zeta / d;
+        for (int c = 0; c < D; ++c) X[n + (int64_t)c * ldx] = xnew[c];
+        out[0] = d; out[1] = zeta;
+    }
+}
+
+// new (N2 x N2) inverse factor from the old (N x N) one: old block copied, identity on the new diagonal, zeros in the new rows
+__global__ void __launch_bounds__(256) model_grow_kernel(const double* __restrict__ Lo, int N, double* __restrict__ Ln, int N2) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (int64_t)N2 * N2) return;
+    const int r = (int)(idx % N2), c = (int)(idx / N2);
+    double v = 0.0;
+    if (r < N && c < N) v = Lo[r + (int64_t)c * N];
+    else if (r == c) v = 1.0;
+    Ln[idx] = v;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -201,7 +381,7 @@ int gpk_gp_nll_grad_dev(gpk_handle h, const double* dX, int n, int D, int64_t ld
     if (!h || n <= 0 || ldx < n) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_nll_grad: bad dimensions");
     if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
     if (nparams < 0 || nparams > D + 2) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, D + 2);
-    return nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev);
+    return nll_grad_single(h, dX, n, D, ldx, dy, theta, has_s, s, nparams, out_dev, info_dev);
 }
 
 int gpk_gp_nll_grad(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y, const double* theta,
@@ -317,9 +497,9 @@ static int model_alloc(gpk_handle h, int n, int D, const double* theta, gpk_mode
     gpk_model m = new (std::nothrow) gpk_model_s();
     if (!m) return GPK_ENOMEM;
     memset(m, 0, sizeof(*m));
-    m->n = n; m->N = gpk_pad(n); m->D = D;
+    m->n = n; m->N = gpk_pad(n); m->D = D; m->ldx = m->N;
     memcpy(m->theta, theta, sizeof(double) * (D + 2));
-    if (cudaMalloc((void**)&m->X, (size_t)n * D * sizeof(double)) != cudaSuccess ||
+    if (cudaMalloc((void**)&m->X, (size_t)m->ldx * D * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&m->Li, (size_t)m->N * m->N * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&m->alpha, (size_t)m->N * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
@@ -352,13 +532,13 @@ int gpk_gp_model_fit(gpk_handle h, const double* X, int n, int D, int64_t ldx, c
     double* dy = (double*)gpk_arena(h, ARENA_X, ((size_t)n + 256) * sizeof(double));
     if (!dy) rc = GPK_ENOMEM;
     double* dout = dy + n;
-    if (!rc) rc = gpk_upload_matrix(h, m->X, X, n, D, ldx);
+    if (!rc) rc = upload_model_x(h, m, X, ldx);
     if (!rc) rc = (cudaMemcpyAsync(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream) == cudaSuccess) ? 0 : GPK_ECUDA;
     Work w;
     if (!rc) rc = make_work(h, n, D, 1, &w);
     if (!rc) rc = gpk_make_problem_params(h, theta, D, has_s, s, &m->pp);
     // factor straight into the model's resident buffers
-    if (!rc) rc = fit_core(h, w, 1, m->X, n, D, n, 0, dy, m->pp, 0, m->Li, m->alpha, dout, 1, h->d_info);
+    if (!rc) rc = fit_core(h, w, 1, m->X, n, D, m->ldx, 0, dy, m->pp, 0, m->Li, m->alpha, dout, 1, h->d_info);
     if (!rc) rc = (cudaMemcpyAsync(h->h_pinned, dout, sizeof(double), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess) ? 0 : GPK_ECUDA;
     if (!rc) rc = gpk_finish_info(h);
     if (rc) { gpk_gp_model_destroy(h, m); return rc; }
@@ -383,7 +563,7 @@ int gpk_gp_model_from_factor(gpk_handle h, const double* X, int n, int D, int64_
     double* dA = (double*)gpk_arena(h, ARENA_A, (size_t)N * N * sizeof(double));
     double* dT = (double*)gpk_arena(h, ARENA_T, gpk_chol_scratch_doubles(N) * sizeof(double));
     if (!dIn || !dA || !dT) rc = GPK_ENOMEM;
-    if (!rc) rc = gpk_upload_matrix(h, m->X, X, n, D, ldx);
+    if (!rc) rc = upload_model_x(h, m, X, ldx);
     if (!rc) rc = gpk_upload_matrix(h, dIn, L, n, n, ldl);
     if (!rc) rc = gpk_load_tri_padded(h, dA, N, dIn, n, n, 0);
     if (!rc) rc = gpk_trtri_lower(h, dA, m->Li, dT, N);
@@ -394,6 +574,74 @@ int gpk_gp_model_from_factor(gpk_handle h, const double* X, int n, int D, int64_
     *out = m;
     return GPK_OK;
 }
+
+// gp/optimization/GPOptimizer.scala:48-71: every outer GP-UCB iteration appends ONE evaluated point to the training set and
+// the reference refits from scratch (preComputeComponents, O(n^3), :51).  With the hyper-parameters unchanged the new factor
+// is the old one bordered by one row, so the resident (L^-1, alpha) are updated in O(n^2): two triangular mat-vecs.
+int gpk_gp_model_append(gpk_handle h, gpk_model m, const double* x_new, double y_new, int has_s, double s, double* ll_delta) {
+    if (!h || !m || !x_new) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_model_append: bad arguments");
+    GPK_CUDA(h, cudaSetDevice(h->device));
+    const int D = m->D;
+    if (m->n == m->N) {   // no padding row left: move to a factor that is one tile larger
+        const int N2 = m->N + GPK_TILE;
+        double *Ln = nullptr, *an = nullptr, *Xn = nullptr;
+        if (cudaMalloc((void**)&Ln, (size_t)N2 * N2 * sizeof(double)) != cudaSuccess ||
+            cudaMalloc((void**)&an, (size_t)N2 * sizeof(double)) != cudaSuccess ||
+            cudaMalloc((void**)&Xn, (size_t)N2 * D * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            if (Ln) cudaFree(Ln);
+            if (an) cudaFree(an);
+            if (Xn) cudaFree(Xn);
+            return gpk_set_error(h, GPK_ENOMEM, "model growth failed (n=%d)", m->n);
+        }
+        model_grow_kernel<<<(unsigned)(((int64_t)N2 * N2 + 255) / 256), 256, 0, h->stream>>>(m->Li, m->N, Ln, N2);
+        GPK_LAUNCH_CHECK(h);
+        GPK_CUDA(h, cudaMemsetAsync(an, 0, (size_t)N2 * sizeof(double), h->stream));
+        GPK_CUDA(h, cudaMemcpyAsync(an, m->alpha, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        GPK_CUDA(h, cudaMemcpy2DAsync(Xn, (size_t)N2 * sizeof(double), m->X, (size_t)m->ldx * sizeof(double), (size_t)m->n * sizeof(double),
+                                      (size_t)D, cudaMemcpyDeviceToDevice, h->stream));
+        GPK_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaFree(m->Li); cudaFree(m->alpha); cudaFree(m->X);
+        m->Li = Ln; m->alpha = an; m->X = Xn; m->N = N2; m->ldx = N2;
+    }
+    const int n = m->n, N = m->N;
+    // x (D), k (N), l (N), w (N), dots (2), out (2), trmv scratch
+    ARENA_OR_FAIL(buf, double*, h, ARENA_IO2, ((size_t)3 * N + D + 8 + gpk_trmv_scratch_doubles(N)) * sizeof(double));
+    double* dx = buf;
+    double* dk = dx + ((D + 1) & ~1);
+    double* dl = dk + N;
+    double* dw = dl + N;
+    double* ddots = dw + N;
+    double* dres = ddots + 2;
+    double* scratch = dres + 2;
+    for (int c = 0; c < D; ++c) h->h_pinned[64 + c] = x_new[c];
+    GPK_CUDA(h, cudaMemcpyAsync(dx, h->h_pinned + 64, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    GPK_CUDA(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
+    int rc = gpk_cov_cross(h, m->X, n, m->ldx, dx, 1, 1, m->pp.cp, dk, N, N, 1);      // k = k(X, x), zero in the padding
+    if (rc) return rc;
+    rc = gpk_trmv_lower(h, m->Li, N, dk, dl, scratch);                                  // l = L^-1 k
+    if (rc) return rc;
+    rc = gpk_colwise_dot(h, dl, N, N, 1, nullptr, ddots, 1);                            // l.l
+    if (rc) return rc;
+    rc = gpk_colwise_dot(h, dk, N, N, 1, m->alpha, ddots + 1, 0);                       // k.alpha
+    if (rc) return rc;
+    rc = gpk_trmv_lower_t(h, m->Li, N, dl, dw);                                         // w = L^-t l
+    if (rc) return rc;
+    // k(x,x) with the i == j noise term (MatrixUtils.scala:63) and the Option sigmaNoise of the fit (GpPredictor.scala:116-117)
+    const double kss = m->pp.cp.sf2 + m->pp.cp.sn2 + (has_s ? s : 0.0);
+    model_append_kernel<<<(n + 256) / 256, 256, 0, h->stream>>>(m->Li, N, n, m->alpha, m->X, m->ldx, D, dx, dw, ddots, kss, y_new,
+                                                                h->d_info, dres);
+    GPK_LAUNCH_CHECK(h);
+    GPK_CUDA(h, cudaMemcpyAsync(h->h_pinned, dres, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    rc = gpk_finish_info(h);
+    if (rc) return rc;
+    m->n = n + 1;
+    // log-likelihood of the enlarged set minus that of the old one: -zeta^2/2 - log d - log(2 pi)/2  (GpPredictor.scala:144-149)
+    if (ll_delta) *ll_delta = -0.5 * h->h_pinned[1] * h->h_pinned[1] - log(h->h_pinned[0]) - 0.9189385332046727;
+    return GPK_OK;
+}
+
+int gpk_gp_model_size(gpk_handle h, gpk_model m) { return m ? m->n : gpk_set_error(h, GPK_EINVAL, "null model"); }
 
 int gpk_gp_model_get_alpha(gpk_handle h, gpk_model m, double* alpha) {
     if (!h || !m || !alpha) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_model_get_alpha: bad arguments");
@@ -420,7 +668,7 @@ int gpk_gp_model_predict(gpk_handle h, gpk_model m, const double* Xs, int ms, in
     int rc = gpk_upload_matrix(h, dXs, Xs, ms, D, ldxs);
     if (rc) return rc;
     // K*^t = k(X, X*) : N x M with zero padding (GpPredictor.scala:53, no noise)
-    rc = gpk_cov_cross(h, m->X, n, n, dXs, ms, ms, cp, dKsT, N, N, M);
+    rc = gpk_cov_cross(h, m->X, n, m->ldx, dXs, ms, ms, cp, dKsT, N, N, M);
     if (rc) return rc;
     // mean = K* alpha (GpPredictor.scala:54)
     rc = gpk_colwise_dot(h, dKsT, N, N, ms, m->alpha, dMean, 0);
@@ -490,7 +738,7 @@ int gpk_gp_model_ucb(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_
     double* dGrad = dVar + M;
     int rc = gpk_upload_matrix(h, dXs, Xs, ms, D, ldxs);
     if (rc) return rc;
-    rc = gpk_cov_cross(h, m->X, n, n, dXs, ms, ms, cp, dKsT, N, N, M);          // k* (GpPredictor.scala:53)
+    rc = gpk_cov_cross(h, m->X, n, m->ldx, dXs, ms, ms, cp, dKsT, N, N, M);     // k* (GpPredictor.scala:53)
     if (rc) return rc;
     rc = gpk_colwise_dot(h, dKsT, N, N, ms, m->alpha, dMean, 0);                 // mean (GpPredictor.scala:54)
     if (rc) return rc;
@@ -508,7 +756,7 @@ int gpk_gp_model_ucb(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_
     g.D = dU; g.ldd = N; g.R = M; g.S = N; g.K = N; g.kb_s = 1;
     rc = gpk_gemm(h, g);
     if (rc) return rc;
-    ucb_grad_kernel<<<dim3(ms, D), 256, 0, h->stream>>>(dKsT, dU, N, n, m->X, dXs, ms, m->alpha, dSq, dMean, cp, k_param, dGrad, dUcb,
+    ucb_grad_kernel<<<dim3(ms, D), 256, 0, h->stream>>>(dKsT, dU, N, n, m->X, m->ldx, dXs, ms, m->alpha, dSq, dMean, cp, k_param, dGrad, dUcb,
                                                         dVar);
     GPK_LAUNCH_CHECK(h);
     GPK_CUDA(h, cudaMemcpyAsync(ucb, dUcb, (size_t)ms * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -540,7 +788,7 @@ int gpk_gp_models_mean(gpk_handle h, const gpk_model* models, int nmodels, const
     if (rc) return rc;
     for (int j = 0; j < nmodels; ++j) {
         gpk_model m = models[j];
-        rc = gpk_cov_cross(h, m->X, m->n, m->n, dXs, ms, ms, m->pp.cp, dKsT, m->N, m->N, M);     // GpPredictor.scala:53
+        rc = gpk_cov_cross(h, m->X, m->n, m->ldx, dXs, ms, ms, m->pp.cp, dKsT, m->N, m->N, M);   // GpPredictor.scala:53
         if (rc) return rc;
         rc = gpk_colwise_dot(h, dKsT, m->N, m->N, ms, m->alpha, dMean + (size_t)j * M, 0);         // :54
         if (rc) return rc;

@@ -9,7 +9,8 @@
 
 #define GPK_TILE 128
 #define GPK_NPIPE 3
-#define GPK_NSIDE 4      // side streams (one per recursion depth, cyclic)
+#define GPK_NSIDE 8      // side streams (one per recursion depth, cyclic; batch group g starts at 4*g)
+#define GPK_NGROUP 2     // batch groups of the batched factorisation: group 0 on the handle's stream, the others on grp[]
 #define GPK_NEVENTS 256  // fork/join event pool (cyclic)  // every internal matrix dimension / leading dimension is a multiple of this
 
 struct gpk_handle_s {
@@ -17,6 +18,7 @@ struct gpk_handle_s {
     cudaStream_t stream;
     bool own_stream;
     cudaStream_t side[GPK_NSIDE];
+    cudaStream_t grp[GPK_NGROUP - 1];   // same priority as the main stream
     cudaStream_t pipe[GPK_NPIPE];   // lowest-priority streams of the pipelined factorisation (trailing updates; inverse rows; K^-1)
     cudaEvent_t evpool[GPK_NEVENTS];
     unsigned ev_next;
@@ -30,8 +32,17 @@ struct gpk_handle_s {
     unsigned func_cfg;  // bitmask: kernels whose dynamic-smem attribute has been set on this device
     void* pp_host;           // host staging for per-problem hyper-parameters (batched calls)
     size_t pp_host_bytes;
+    // CUDA-graph replay of the single-problem evaluation (gpk_gp.cu: the evaluation is ~350 launches on 8 streams; an
+    // optimiser calls it over and over with the same buffers and new hyper-parameters)
+    int graph_mode;               // 0 off, 1 capture on the second call with one signature and replay from then on
+    unsigned arena_epoch;         // bumped whenever an arena is (re)allocated: a cached graph holds arena pointers
+    struct gpk_eval_graph* eval_graph;
+    struct gpk_capture_log* cap;  // non-null while capturing: every kernel node with the priority of the stream it came from
+    int prio_main, prio_side, prio_pipe;
     char err[512];
 };
+void gpk_capture_note(gpk_handle h);    // gpk_gp.cu
+void gpk_eval_graph_drop(gpk_handle h); // gpk_gp.cu: forget the cached graph (handle teardown)
 
 enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7, ARENA_PP = 8, ARENA_INFO = 9, ARENA_GEMV = 10, ARENA_KINV = 11, GPK_NARENA = 12 };
 
@@ -53,6 +64,7 @@ int gpk_finish_info(gpk_handle h);  // sync, read h->d_info[0], map to GPK_ENOTP
 #define GPK_LAUNCH_CHECK(h)                                                                       \
     do {                                                                                          \
         (h)->launches++;                                                                          \
+        if ((h)->cap) gpk_capture_note(h);                                                        \
         cudaError_t e__ = cudaGetLastError();                                                     \
         if (e__ != cudaSuccess)                                                                   \
             return gpk_set_error((h), GPK_ECUDA, "kernel launch failed: %s (%s:%d)",              \

@@ -2,8 +2,9 @@
 
 The O(n^2)/O(n^3) work of the inner loop -- fitting the surrogate (GPOptimizer.scala:51), and per candidate point the
 posterior, the two n x D kernel-derivative matrices and `inversedL * trainTestDerMtx` (GPOptimizer.scala:85-103) -- runs in
-libgpk against a device-resident model (`gpk_gp_model_fit` once per outer iteration, `gpk_gp_model_ucb` per evaluation,
-any number of candidate points per call).  What stays on the host is control flow only: the random grid, the restarts'
+libgpk against a device-resident model (`gpk_gp_model_fit` once, `gpk_gp_model_append` for the point every outer iteration
+adds -- the hyper-parameters do not change inside the loop, so the refit of GPOptimizer.scala:51 is a bordered update --
+and `gpk_gp_model_ucb` per evaluation, any number of candidate points per call).  What stays on the host is control flow only: the random grid, the restarts'
 start points and the gradient optimiser's line search, exactly the parts the reference delegates to Breeze / scala.util.Random.
 """
 from __future__ import annotations
@@ -91,9 +92,11 @@ class GPOptimizer:
         evaluated = self.evaluateGridPoints(pointSet, func)
         hp = (self.gpPredictor.obtainOptimalHyperParams(pointSet, self.noise, evaluated, True)     # GPOptimizer.scala:42-46
               if params.optimizeHpOnInitGrid else self.hyperParams)
-        for _ in range(m):                                                            # GPOptimizer.scala:48-77
-            model = self.gpPredictor.fit(pointSet, self.noise, evaluated, hp)         # preComputeComponents, resident
-            try:
+        # preComputeComponents (GPOptimizer.scala:51) once; every later iteration's refit differs from this model by the one
+        # appended point (same hyper-parameters, same noise), which FittedGp.append applies in place
+        model = self.gpPredictor.fit(pointSet, self.noise, evaluated, hp)
+        try:
+            for it in range(m):                                                       # GPOptimizer.scala:48-77
                 mean = pointSet.mean(axis=0)                                          # StatsUtils.scala:61-72
                 diff = pointSet - mean
                 cov = diff.T @ diff / pointSet.shape[0]
@@ -105,14 +108,16 @@ class GPOptimizer:
                         best_pt, best_ucb = pt, val
                 if best_pt is None:
                     best_pt = self.rng.multivariate_normal(mean, cov, method="svd")
-            finally:
-                model.close()
-            try:                                                                      # :64-71
-                v = func(np.array(best_pt))
+                try:                                                                  # :64-71
+                    v = func(np.array(best_pt))
+                except Exception:
+                    continue                                                          # point set unchanged (:70)
+                if it + 1 < m:                    # the reference refits (and may throw from `cholesky`, :51) only if another iteration follows
+                    model.append(best_pt, v)
                 pointSet = np.vstack([pointSet, best_pt[None, :]])
                 evaluated = np.concatenate([evaluated, [v]])
-            except Exception:
-                pass
+        finally:
+            model.close()
         i = int(np.argmax(evaluated))                                                 # :73-79 (first maximum)
         return pointSet[i].copy(), float(evaluated[i])
 

@@ -188,8 +188,8 @@ def models_mean(models, testData) -> np.ndarray:
 class FittedGp:
     """Opaque device token for (X, L^-1, alpha, theta) -- SURVEY.md 8(b) 'ownership'."""
 
-    def __init__(self, handle, token, n, D, ll=None):
-        self.handle, self._m, self.n, self.D, self.logLikelihood = handle, token, n, D, ll
+    def __init__(self, handle, token, n, D, ll=None, sigmaNoise=None):
+        self.handle, self._m, self.n, self.D, self.logLikelihood, self.sigmaNoise = handle, token, n, D, ll, sigmaNoise
 
     @classmethod
     def fit(cls, handle, trainingData, targets, theta, sigmaNoise=None):
@@ -201,7 +201,7 @@ class FittedGp:
         handle.check(handle.lib.gpk_gp_model_fit(handle.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(theta),
                                                  int(sigmaNoise is not None), float(sigmaNoise or 0.0), C.byref(tok),
                                                  C.addressof(ll)))
-        return cls(handle, tok, n, D, ll.value)
+        return cls(handle, tok, n, D, ll.value, sigmaNoise)
 
     @classmethod
     def from_factor(cls, handle, trainingData, l, alphaVec, kernelFunc):
@@ -235,6 +235,21 @@ class FittedGp:
         self.handle.check(self.handle.lib.gpk_gp_model_predict(self.handle.h, self._m, _lib.ptr(Xs), m, m, 0, _lib.ptr(mean), None, m,
                                                                None, self.n))
         return mean
+
+    def append(self, point, target: float) -> None:
+        """One more training point with unchanged hyper-parameters: the GP-UCB outer loop (GPOptimizer.scala:48-71) refits with
+        preComputeComponents every iteration; here the resident L^-1 and alpha get the bordered row in O(n^2).  Raises
+        NotPositiveDefiniteError (minor = n+1, model unchanged) where the refit's `cholesky` would throw."""
+        x = np.ascontiguousarray(point, dtype=np.float64).ravel()
+        if x.size != self.D:
+            raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, f"requirement failed: point has {x.size} coordinates, model has {self.D}")
+        d = C.c_double()
+        s = self.sigmaNoise
+        self.handle.check(self.handle.lib.gpk_gp_model_append(self.handle.h, self._m, _lib.ptr(x), float(target), int(s is not None),
+                                                              float(s or 0.0), C.addressof(d)))
+        self.n += 1
+        if self.logLikelihood is not None:
+            self.logLikelihood += d.value
 
     @property
     def alphaVec(self) -> np.ndarray:

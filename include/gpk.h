@@ -51,6 +51,11 @@ int gpk_synchronize(gpk_handle h);
 /* number of kernel launches issued through this handle since creation (bench.py "gpu_launches") */
 int64_t gpk_launch_count(gpk_handle h);
 const char* gpk_version(void);
+/* Repeated gpk_gp_nll_grad[_dev] calls with the same buffers and shape (an optimiser's objective,
+ * GpPredictor.scala:126-142) are captured into a CUDA graph on the second call and replayed afterwards; new
+ * hyper-parameters reach the replay through device memory.  on = 0 keeps every call on eager launches
+ * (default 1, or the GPK_GRAPH environment variable).  Results are identical either way. */
+int gpk_set_graph_mode(gpk_handle h, int on);
 
 /* ---- fine-grained MatrixUtils replacements ---------------------------------------------------- */
 /* utils/MatrixUtils.scala:57-70  buildKernelMatrix(kernel, data): symmetric n x n,
@@ -121,6 +126,15 @@ int gpk_gp_model_from_factor(gpk_handle h, const double* X, int n, int D, int64_
 int gpk_gp_model_destroy(gpk_handle h, gpk_model m);
 /* alphaVec = L^t \\ (L \\ targets) of the resident model (GpPredictor.scala:121-122), n doubles. */
 int gpk_gp_model_get_alpha(gpk_handle h, gpk_model m, double* alpha);
+/* gp/optimization/GPOptimizer.scala:48-71: each GP-UCB iteration adds ONE evaluated point (x_new: D doubles, y_new) to the
+ * training set and the reference refits from scratch (preComputeComponents, :51).  This updates the resident L^-1 and alpha
+ * by the bordered row instead (O(n^2)); afterwards the model equals gpk_gp_model_fit on the enlarged set with the same
+ * hyper-parameters and the same Option sigmaNoise.  ll_delta (may be NULL) = logLikelihood(new set) - logLikelihood(old set).
+ * GPK_ENOTPD (gpk_last_info = n+1) when the enlarged matrix is not positive definite; the model is then unchanged. */
+int gpk_gp_model_append(gpk_handle h, gpk_model m, const double* x_new, double y_new, int has_sigma_noise,
+                        double sigma_noise, double* ll_delta);
+/* number of training points of the resident model */
+int gpk_gp_model_size(gpk_handle h, gpk_model m);
 /* gp/regression/GpPredictor.scala:45-58 computePosterior: mean (m), sigma (m x m full if
  * want_full_cov, else only the diagonal in sigma[0..m-1]), V = L^-1 K*^t (n x m, may be NULL).
  * The sigma diagonal includes noiseVar^2 (MatrixUtils.scala:63 via GpPredictor.scala:56). */

@@ -59,3 +59,53 @@ def test_gp_optimizer_finds_the_maximum_of_a_smooth_function():
     assert val2 <= 0.0 and best2.shape == (2,)
     with pytest.raises(ValueError):
         opt.maximize(f, gp.GPOInput(ranges=[(-1.0, 1.0)], mParam=0, cParam=1, kParam=1.0))
+
+
+# ---- GPOptimizer.scala:48-71: one evaluated point joins the training set per iteration --------------------------------
+@pytest.mark.parametrize("n0,D,sigma_noise", [(30, 2, None), (381, 8, None), (254, 3, 0.02)])
+def test_append_equals_refit(n0, D, sigma_noise):
+    """The resident model after k appends equals the reference's refit on the enlarged set (preComputeComponents,
+    GpPredictor.scala:104-124): alpha, posterior mean / variance and the log-likelihood, 1e-9.  n0 = 381 / 254 walk through a
+    full 128-tile (n == N: the factor moves to a larger buffer) while appending."""
+    k = 6
+    X, y, th = orc.make_c2(n=n0 + k, D=D, seed=11 + n0)
+    pred = gp.GpPredictor(gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1])))
+    model = pred.fit(X[:n0], sigma_noise, y[:n0], th)
+    Xs = np.random.default_rng(n0).uniform(0, 1, size=(9, D))
+    for j in range(k):
+        model.append(X[n0 + j], y[n0 + j])
+        n = n0 + j + 1
+        assert model.n == n
+        if j in (0, 2, k - 1):
+            L, alpha = orc.lit_precompute(X[:n], y[:n], th, sigma_noise)
+            a = model.alphaVec
+            assert a.shape == (n,)
+            assert np.all(np.abs(a - alpha) <= 1e-9 * np.abs(alpha).max())
+            dist, _ = model.computePosterior(Xs)
+            m_o, S_o, _ = orc.lit_compute_posterior(X[:n], Xs, L, alpha, th)
+            assert np.all(np.abs(dist.mean - m_o) <= 1e-9 * np.maximum(np.abs(m_o), 1e-3))
+            assert np.all(np.abs(np.diag(dist.sigma) - np.diag(S_o)) <= 1e-9 * np.abs(np.diag(S_o)))
+            ll_o = orc.lit_loglik(alpha, L, y[:n])
+            assert abs(model.logLikelihood - ll_o) <= 1e-9 * abs(ll_o)
+            u, g, _, _ = gp.ucb_with_gradient(model, Xs[:2], 1.5)
+            u_o, g_o, _, _ = orc.lit_ucb_with_grad(X[:n], L, alpha, th, Xs[1], 1.5)
+            assert abs(u[1] - u_o) <= 1e-9 * max(abs(u_o), 1e-3) and close(g[1], g_o)
+    model.close()
+
+
+def test_append_not_positive_definite_leaves_the_model_unchanged():
+    th = orc.pack_theta(1.0, [0.7, 0.7], 0.0)           # no noise: a repeated input makes the enlarged K exactly singular
+    X, y = np.array([[0.3, 0.8]]), np.array([0.5])
+    pred = gp.GpPredictor(gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1])))
+    model = pred.fit(X, None, y, th)
+    a0 = model.alphaVec
+    with pytest.raises(gp.NotPositiveDefiniteError) as ei:   # k = 1, l = 1, d^2 = 1 - 1 = 0: `cholesky` of the refit throws
+        model.append(X[0], 0.3)
+    assert ei.value.minor == 2 and model.n == 1
+    assert np.array_equal(model.alphaVec, a0)
+    with pytest.raises(ValueError):
+        model.append(np.zeros(3), 0.0)
+    model.append(np.array([1.1, -0.4]), 0.3)            # a fresh point still goes in
+    L, alpha = orc.lit_precompute(np.vstack([X, [[1.1, -0.4]]]), np.append(y, 0.3), th)
+    assert np.all(np.abs(model.alphaVec - alpha) <= 1e-9 * np.abs(alpha).max())
+    model.close()
