@@ -5,6 +5,7 @@ the host-side mirror of the reference's Scala interface for that path (same name
 and error behaviour), used by the parity tests and the benchmark:
 
     utils.KernelRequisites  ->  gp_algos_b200.kernel_requisites  (GaussianRbfParams, GaussianRbfKernel)
+    gp.regression.Co2Prediction -> gp_algos_b200.co2_prediction  (Co2HyperParams, Co2Kernel: the second closed-form kernel)
     utils.MatrixUtils       ->  gp_algos_b200.matrix_utils       (buildKernelMatrix, forwardSolve, ...)
     gp.regression.GpPredictor -> gp_algos_b200.gp_predictor      (GpPredictor, PredictionInput, ...)
     gp.classification.*      ->  gp_algos_b200.ep_classification (EpParameterEstimator, GpClassifier, ...)
@@ -17,6 +18,7 @@ There is no CPU fallback: importing works anywhere, but every numeric call raise
 CUDA device is missing.
 """
 from .kernel_requisites import GaussianRbfKernel, GaussianRbfParams  # noqa: F401
+from .co2_prediction import Co2HyperParams, Co2Kernel, co2DataToYearWithValue  # noqa: F401
 from .gp_predictor import GpPredictor, PredictionInput, PredictionTrainingInput, GaussianDistribution  # noqa: F401
 from . import matrix_utils as MatrixUtils  # noqa: F401
 from . import batched  # noqa: F401
@@ -28,5 +30,5 @@ from .gp_ukf import (UnscentedKalmanFilter, GPUnscentedKalmanFilter, UnscentedTr
                      SsmModel, FilteringOutput)
 from ._lib import GpkError, NotPositiveDefiniteError, MatrixNotSymmetricError, lib_path  # noqa: F401
 
-__all__ = ["GaussianRbfKernel", "GaussianRbfParams", "GpPredictor", "PredictionInput", "PredictionTrainingInput",
+__all__ = ["GaussianRbfKernel", "GaussianRbfParams", "Co2Kernel", "Co2HyperParams", "GpPredictor", "PredictionInput", "PredictionTrainingInput",
            "GaussianDistribution", "MatrixUtils", "GpkError", "NotPositiveDefiniteError", "MatrixNotSymmetricError"]

@@ -65,6 +65,9 @@ def load():
         lib.gpk_destroy.argtypes = [C.c_void_p]
         lib.gpk_synchronize.argtypes = [C.c_void_p]
         lib.gpk_set_graph_mode.argtypes = [C.c_void_p, C.c_int]
+        lib.gpk_set_kernel_family.argtypes = [C.c_void_p, C.c_int]
+        lib.gpk_get_kernel_family.argtypes = [C.c_void_p]
+        lib.gpk_theta_length.argtypes = [C.c_void_p, C.c_int]
         vp, ci, cd = C.c_void_p, C.c_int, C.c_double
         lib.gpk_cov_se_ard.argtypes = [vp, vp, ci, ci, _i64, vp, vp, _i64]
         lib.gpk_cov_se_ard_dev.argtypes = [vp, vp, ci, ci, _i64, vp, vp, _i64]
@@ -139,6 +142,11 @@ class Handle:
         """CUDA-graph replay of repeated logLikelihoodWithDerivatives calls (include/gpk.h); on by default."""
         self.check(self.lib.gpk_set_graph_mode(self._h, 1 if on else 0))
 
+    def kernel_family(self, family: int):
+        """`with h.kernel_family(GPK_KERNEL_CO2): ...` -- how the (D, theta) arguments of the enclosed calls are read
+        (include/gpk.h); the handle goes back to its previous family afterwards."""
+        return _FamilyScope(self, int(family))
+
     def synchronize(self):
         self.check(self.lib.gpk_synchronize(self._h))
 
@@ -152,6 +160,20 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+
+class _FamilyScope:
+    def __init__(self, handle, family):
+        self.h, self.family = handle, family
+
+    def __enter__(self):
+        self.prev = self.h.lib.gpk_get_kernel_family(self.h._h)
+        self.h.check(self.h.lib.gpk_set_kernel_family(self.h._h, self.family))
+        return self.h
+
+    def __exit__(self, *exc):
+        self.h.lib.gpk_set_kernel_family(self.h._h, self.prev)
+        return False
 
 
 _default = {}

@@ -155,6 +155,13 @@ int gpk_destroy(gpk_handle h) {
 const char* gpk_last_error(gpk_handle h) { return h ? h->err : "null handle"; }
 int gpk_last_info(gpk_handle h) { return h ? h->last_info : 0; }
 int64_t gpk_launch_count(gpk_handle h) { return h ? h->launches : 0; }
+int gpk_set_kernel_family(gpk_handle h, int family) {
+    if (!h || (family != GPK_KERNEL_SE_ARD && family != GPK_KERNEL_CO2)) return gpk_set_error(h, GPK_EINVAL, "unknown kernel family %d", family);
+    h->kernel_family = family;
+    return GPK_OK;
+}
+int gpk_get_kernel_family(gpk_handle h) { return h ? h->kernel_family : GPK_EINVAL; }
+int gpk_theta_length(gpk_handle h, int D) { return h ? gpk_theta_len(h, D) : GPK_EINVAL; }
 int gpk_set_graph_mode(gpk_handle h, int on) {
     if (!h) return GPK_EINVAL;
     h->graph_mode = on ? 1 : 0;
@@ -224,8 +231,8 @@ int gpk_cov_cross_se_ard(gpk_handle h, const double* X1, int m, int64_t ldx1, co
 int gpk_cov_deriv_se_ard(gpk_handle h, int param_num, const double* X, int n, int D, int64_t ldx, const double* theta,
                          double* dKout, int64_t ldk) {
     if (!h || n < 0 || ldx < n || ldk < n) return gpk_set_error(h, GPK_EINVAL, "gpk_cov_deriv: bad dimensions");
-    if (param_num < 1 || param_num > D + 2)
-        return gpk_set_error(h, GPK_EINVAL, "scala.MatchError: hyper-parameter %d outside 1..%d", param_num, D + 2);
+    if (param_num < 1 || param_num > gpk_theta_len(h, D))
+        return gpk_set_error(h, GPK_EINVAL, "scala.MatchError: hyper-parameter %d outside 1..%d", param_num, gpk_theta_len(h, D));
     if (n == 0) return GPK_OK;
     GPK_CUDA(h, cudaSetDevice(h->device));
     ARENA_OR_FAIL(dX, double*, h, ARENA_X, (size_t)n * D * sizeof(double));

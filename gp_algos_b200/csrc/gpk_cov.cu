@@ -44,7 +44,9 @@ __device__ __forceinline__ void store2(double* p, double a, double b, bool ok0, 
     }
 }
 
-template <int MODE>
+// KIND = gpk_kernel_family: GPK_KERNEL_SE_ARD accumulates the scaled squared distance over the feature dimensions;
+// GPK_KERNEL_CO2 (1-D inputs) keeps the plain difference and evaluates Co2Prediction.scala:38-56 on it.
+template <int MODE, int KIND>
 __global__ void __launch_bounds__(256) cov_se_ard_kernel(const CovArgs a0) {
     // per-problem view (blockIdx.z); hyper-parameters by value (single problem) or from the device array (batched)
     struct View { const double* X1; const double* X2; double* K; int64_t ldx1, ldx2, ldk; int m, n, mp, np; const CovParams& cp; };
@@ -85,8 +87,12 @@ __global__ void __launch_bounds__(256) cov_se_ard_kernel(const CovArgs a0) {
             for (int b = 0; b < 8; ++b) {
                 const double xv = xj[d][ty + 8 * b];
                 const double f0 = __dsub_rn(x0, xv), f1 = __dsub_rn(x1, xv);
-                r[0][b] = __dadd_rn(r[0][b], __dmul_rn(__dmul_rn(f0, inv), f0));
-                r[1][b] = __dadd_rn(r[1][b], __dmul_rn(__dmul_rn(f1, inv), f1));
+                if (KIND == GPK_KERNEL_CO2) {
+                    r[0][b] = f0; r[1][b] = f1;     // D == 1: the difference itself
+                } else {
+                    r[0][b] = __dadd_rn(r[0][b], __dmul_rn(__dmul_rn(f0, inv), f0));
+                    r[1][b] = __dadd_rn(r[1][b], __dmul_rn(__dmul_rn(f1, inv), f1));
+                }
             }
         }
     }
@@ -99,7 +105,13 @@ __global__ void __launch_bounds__(256) cov_se_ard_kernel(const CovArgs a0) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int gi = gi0 + q;
-            double val = __dmul_rn(a.cp.sf2, exp(__dmul_rn(-0.5, r[q][b])));
+            double val;
+            if (KIND == GPK_KERNEL_CO2) {
+                Co2Terms t;
+                val = co2_value(a.cp.inv_ls2, r[q][b], t);
+            } else {
+                val = __dmul_rn(a.cp.sf2, exp(__dmul_rn(-0.5, r[q][b])));
+            }
             if (MODE != MODE_CROSS && gi == gj) {
                 val = __dadd_rn(val, a.cp.sn2);
                 if (a.cp.extra_diag != 0.0) val = __dadd_rn(val, a.cp.extra_diag);
@@ -134,6 +146,15 @@ __global__ void cov_deriv_kernel(int param_num, const double* X, int n, int64_t 
     const int j = blockIdx.x;
     if (i >= n || j >= n) return;
     const int D = cp.D;
+    if (cp.kind == GPK_KERNEL_CO2) {   // Co2Prediction.scala:66-137
+        Co2Terms t;
+        double dk[GPK_CO2_NPARAMS];
+        co2_value(cp.inv_ls2, __dsub_rn(X[i], X[j]), t);
+        co2_derivs(cp.inv_ls2, t, dk);
+        dk[10] = (i == j) ? 2 * cp.inv_ls2[10] : 0.0;
+        dK[i + (int64_t)j * ldk] = dk[param_num - 1];
+        return;
+    }
     double r = 0.0;
     for (int d = 0; d < D; ++d) {
         const double f = __dsub_rn(X[i + (int64_t)d * ldx], X[j + (int64_t)d * ldx]);
@@ -157,6 +178,11 @@ __global__ void cov_deriv_kernel(int param_num, const double* X, int n, int64_t 
 int gpk_make_problem_params(gpk_handle h, const double* theta, int D, int has_sigma_noise, double sigma_noise, ProblemParams* out) {
     int rc = gpk_make_cov_params(h, theta, D, has_sigma_noise, sigma_noise, &out->cp);
     if (rc) return rc;
+    if (out->cp.kind == GPK_KERNEL_CO2) {   // the trace kernel accumulates the full derivative: only the 1/2 of the trace is left
+        memset(out->gscale, 0, sizeof(out->gscale));
+        for (int p = 0; p < GPK_CO2_NPARAMS; ++p) out->gscale[p] = 0.5;
+        return GPK_OK;
+    }
     const double sf = theta[0], sn = theta[D + 1];
     memset(out->gscale, 0, sizeof(out->gscale));
     out->gscale[0] = sf;                                          // 1/2 * 2 sf
@@ -172,6 +198,20 @@ int gpk_make_cov_params(gpk_handle h, const double* theta, int D, int has_sigma_
     if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
     memset(out, 0, sizeof(*out));
     out->D = D;
+    out->kind = h ? h->kernel_family : GPK_KERNEL_SE_ARD;
+    if (out->kind == GPK_KERNEL_CO2) {
+        // require(obj1.length == 1 && obj2.length == 1, "This kernel is applicable only for 1D objects") Co2Prediction.scala:39
+        if (D != 1) return gpk_set_error(h, GPK_EINVAL, "requirement failed: This kernel is applicable only for 1D objects");
+        double* par = out->inv_ls2;
+        for (int p = 0; p < GPK_CO2_NPARAMS; ++p) par[p] = theta[p];
+        par[11] = pow(theta[1], -3); par[12] = pow(theta[3], -3); par[13] = pow(theta[4], -3); par[14] = pow(theta[6], -3);
+        par[15] = pow(theta[9], -3);
+        // k(x,x): every exp / pow factor is exactly 1, summed in the order of Co2Prediction.scala:55
+        out->sf2 = ((theta[0] * theta[0] + theta[2] * theta[2]) + theta[5] * theta[5]) + theta[8] * theta[8];
+        out->sn2 = theta[10] * theta[10];
+        out->extra_diag = has_sigma_noise ? sigma_noise : 0.0;
+        return GPK_OK;
+    }
     out->sf2 = theta[0] * theta[0];
     out->sn2 = theta[D + 1] * theta[D + 1];
     out->extra_diag = has_sigma_noise ? sigma_noise : 0.0;
@@ -185,7 +225,8 @@ int gpk_cov_sym_full(gpk_handle h, const double* dX, int n, int64_t ldx, const C
     a.X1 = dX; a.ldx1 = ldx; a.m = n; a.X2 = dX; a.ldx2 = ldx; a.n = n; a.K = dK; a.ldk = ldk; a.mp = n; a.np = n; a.cp = cp;
     a.strideX1 = a.strideX2 = a.strideK = 0; a.pp = nullptr;
     const int t = (n + CT - 1) / CT;
-    cov_se_ard_kernel<MODE_SYM_FULL><<<dim3(t, t), 256, 0, h->stream>>>(a);
+    if (cp.kind == GPK_KERNEL_CO2) cov_se_ard_kernel<MODE_SYM_FULL, GPK_KERNEL_CO2><<<dim3(t, t), 256, 0, h->stream>>>(a);
+    else cov_se_ard_kernel<MODE_SYM_FULL, GPK_KERNEL_SE_ARD><<<dim3(t, t), 256, 0, h->stream>>>(a);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }
@@ -196,7 +237,8 @@ int gpk_cov_sym_lower_padded(gpk_handle h, const double* dX, int n, int64_t ldx,
     a.X1 = dX; a.ldx1 = ldx; a.m = n; a.X2 = dX; a.ldx2 = ldx; a.n = n; a.K = dK; a.ldk = N; a.mp = N; a.np = N; a.cp = cp;
     a.strideX1 = a.strideX2 = strideX; a.strideK = (int64_t)N * N; a.pp = pp_dev;
     const int t = N / CT;
-    cov_se_ard_kernel<MODE_SYM_LOWER_PAD><<<dim3(t, t, batch), 256, 0, h->stream>>>(a);
+    if (cp.kind == GPK_KERNEL_CO2) cov_se_ard_kernel<MODE_SYM_LOWER_PAD, GPK_KERNEL_CO2><<<dim3(t, t, batch), 256, 0, h->stream>>>(a);
+    else cov_se_ard_kernel<MODE_SYM_LOWER_PAD, GPK_KERNEL_SE_ARD><<<dim3(t, t, batch), 256, 0, h->stream>>>(a);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }
@@ -210,7 +252,9 @@ int gpk_cov_cross(gpk_handle h, const double* dX1, int m, int64_t ldx1, const do
     CovArgs a;
     a.X1 = dX1; a.ldx1 = ldx1; a.m = m; a.X2 = dX2; a.ldx2 = ldx2; a.n = n; a.K = dK; a.ldk = ldk; a.mp = mp; a.np = np; a.cp = cp;
     a.strideX1 = strideX1; a.strideX2 = strideX2; a.strideK = strideK; a.pp = pp_dev;
-    cov_se_ard_kernel<MODE_CROSS><<<dim3((mp + CT - 1) / CT, (np + CT - 1) / CT, batch), 256, 0, h->stream>>>(a);
+    const dim3 grid((mp + CT - 1) / CT, (np + CT - 1) / CT, batch);
+    if (cp.kind == GPK_KERNEL_CO2) cov_se_ard_kernel<MODE_CROSS, GPK_KERNEL_CO2><<<grid, 256, 0, h->stream>>>(a);
+    else cov_se_ard_kernel<MODE_CROSS, GPK_KERNEL_SE_ARD><<<grid, 256, 0, h->stream>>>(a);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }

@@ -27,7 +27,7 @@ struct gpk_capture_log {
 };
 struct gpk_eval_graph {
     const double* dX; const double* dy; double* out; int* info;   // signature of the captured call
-    int n, D, nparams; int64_t ldx; unsigned arena_epoch;
+    int n, D, nparams, family; int64_t ldx; unsigned arena_epoch;
     int calls;               // eager calls seen with this signature
     int failed;              // capture was refused once: stay eager
     cudaGraphExec_t exec;    // null until captured
@@ -126,7 +126,7 @@ int stage_params(gpk_handle h, const double* thetas, int D, int has_s, double s,
     }
     ProblemParams* hp = (ProblemParams*)h->pp_host;
     for (int b = 0; b < B; ++b) {
-        int rc = gpk_make_problem_params(h, thetas + (size_t)b * (D + 2), D, has_s, s, &hp[b]);
+        int rc = gpk_make_problem_params(h, thetas + (size_t)b * gpk_theta_len(h, D), D, has_s, s, &hp[b]);
         if (rc) return rc;
     }
     *first = hp[0];
@@ -171,7 +171,7 @@ int nll_grad_core(gpk_handle h, int B, const double* dX, int n, int D, int64_t l
         const int bc = (B - b0 < w.B) ? B - b0 : w.B;
         ProblemParams pp0;
         if (on_dev) pp0 = *pp_single;
-        else rc = stage_params(h, thetas + (size_t)b0 * (D + 2), D, has_s, s, bc, w.pp_dev, &pp0);
+        else rc = stage_params(h, thetas + (size_t)b0 * gpk_theta_len(h, D), D, has_s, s, bc, w.pp_dev, &pp0);
         if (rc) return rc;
         const double* X = dX + b0 * strideX;
         int* info = info_dev ? info_dev + b0 : (B == 1 ? h->d_info : w.info_dev);
@@ -215,12 +215,12 @@ int nll_grad_single(gpk_handle h, const double* dX, int n, int D, int64_t ldx, c
     if (nparams > 0 && gpk_use_pipelined(w.N, 1) && !gpk_arena(h, ARENA_KINV, (size_t)w.N * w.N * sizeof(double))) return GPK_ENOMEM;
     gpk_eval_graph* g = h->eval_graph;
     if (!g || g->dX != dX || g->dy != dy || g->out != out_dev || g->info != info_dev || g->n != n || g->D != D ||
-        g->nparams != nparams || g->ldx != ldx || g->arena_epoch != h->arena_epoch) {
+        g->nparams != nparams || g->ldx != ldx || g->arena_epoch != h->arena_epoch || g->family != h->kernel_family) {
         gpk_eval_graph_drop(h);
         g = new (std::nothrow) gpk_eval_graph();
         if (!g) return gpk_set_error(h, GPK_ENOMEM, "host allocation failed");
         memset(g, 0, sizeof(*g));
-        g->dX = dX; g->dy = dy; g->out = out_dev; g->info = info_dev; g->n = n; g->D = D; g->nparams = nparams; g->ldx = ldx;
+        g->dX = dX; g->dy = dy; g->out = out_dev; g->info = info_dev; g->n = n; g->D = D; g->nparams = nparams; g->ldx = ldx; g->family = h->kernel_family;
         g->arena_epoch = h->arena_epoch;
         h->eval_graph = g;
     }
@@ -380,7 +380,7 @@ int gpk_gp_nll_grad_dev(gpk_handle h, const double* dX, int n, int D, int64_t ld
                         int has_s, double s, int nparams, double* out_dev, int* info_dev) {
     if (!h || n <= 0 || ldx < n) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_nll_grad: bad dimensions");
     if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
-    if (nparams < 0 || nparams > D + 2) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, D + 2);
+    if (nparams < 0 || nparams > gpk_theta_len(h, D)) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, gpk_theta_len(h, D));
     return nll_grad_single(h, dX, n, D, ldx, dy, theta, has_s, s, nparams, out_dev, info_dev);
 }
 
@@ -410,7 +410,7 @@ int gpk_gp_nll_grad_batched_dev(gpk_handle h, int B, const double* dX, int n, in
                                 int* info_dev) {
     if (!h || B <= 0 || n <= 0 || ldx < n || !info_dev) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_nll_grad_batched: bad arguments");
     if (D < 1 || D > GPK_MAX_D) return gpk_set_error(h, GPK_EINVAL, "feature dimension D=%d outside 1..%d", D, GPK_MAX_D);
-    if (nparams < 0 || nparams > D + 2) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, D + 2);
+    if (nparams < 0 || nparams > gpk_theta_len(h, D)) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, gpk_theta_len(h, D));
     return nll_grad_core(h, B, dX, n, D, ldx, strideX, dy, thetas, has_s, s, nparams, out_dev, info_dev);
 }
 
@@ -498,7 +498,7 @@ static int model_alloc(gpk_handle h, int n, int D, const double* theta, gpk_mode
     if (!m) return GPK_ENOMEM;
     memset(m, 0, sizeof(*m));
     m->n = n; m->N = gpk_pad(n); m->D = D; m->ldx = m->N;
-    memcpy(m->theta, theta, sizeof(double) * (D + 2));
+    memcpy(m->theta, theta, sizeof(double) * gpk_theta_len(h, D));
     if (cudaMalloc((void**)&m->X, (size_t)m->ldx * D * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&m->Li, (size_t)m->N * m->N * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&m->alpha, (size_t)m->N * sizeof(double)) != cudaSuccess) {
@@ -722,6 +722,8 @@ int gpk_gp_model_ucb(gpk_handle h, gpk_model m, const double* Xs, int ms, int64_
                      int64_t ldg, double* mean, double* var) {
     if (!h || !m || !Xs || !ucb || ms <= 0 || ldxs < ms || (grad && ldg < ms))
         return gpk_set_error(h, GPK_EINVAL, "gpk_gp_model_ucb: bad dimensions");
+    if (m->pp.cp.kind != GPK_KERNEL_SE_ARD)   // Co2Kernel.gradient is `???` (Co2Prediction.scala:62-64)
+        return gpk_set_error(h, GPK_EINVAL, "scala.NotImplementedError: the kernel has no gradient with respect to its inputs");
     GPK_CUDA(h, cudaSetDevice(h->device));
     const int n = m->n, N = m->N, D = m->D, M = gpk_pad(ms);
     const CovParams& cp = m->pp.cp;
@@ -840,7 +842,7 @@ int gpk_gp_predict_batched(gpk_handle h, int B, const double* X, int n, int D, i
     for (int b0 = 0; b0 < B && !rc; b0 += Bc) {
         const int bc = (B - b0 < Bc) ? B - b0 : Bc;
         ProblemParams pp0;
-        rc = stage_params(h, thetas + (size_t)b0 * (D + 2), D, has_s, s, bc, w.pp_dev, &pp0);
+        rc = stage_params(h, thetas + (size_t)b0 * gpk_theta_len(h, D), D, has_s, s, bc, w.pp_dev, &pp0);
         for (int b = 0; b < (strideX ? bc : 1) && !rc; ++b)
             rc = gpk_upload_matrix(h, dX + (size_t)b * n * D, X + (strideX ? (b0 + b) * strideX : 0), n, D, ldx);
         for (int b = 0; b < (strideXs ? bc : 1) && !rc; ++b)
@@ -874,8 +876,10 @@ int gpk_gp_predict_batched(gpk_handle h, int B, const double* X, int n, int D, i
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { rc = gpk_set_error(h, GPK_ECUDA, "batched predict: %s", cudaGetErrorString(e)); break; }
         for (int b = 0; b < bc; ++b) {
-            const double* th = thetas + (size_t)(b0 + b) * (D + 2);
-            const double kss = th[0] * th[0] + th[D + 1] * th[D + 1];  // k(x*,x*) incl. the i==j noise term (MatrixUtils.scala:63)
+            const double* th = thetas + (size_t)(b0 + b) * gpk_theta_len(h, D);
+            CovParams cpb;
+            gpk_make_cov_params(h, th, D, 0, 0.0, &cpb);
+            const double kss = cpb.sf2 + cpb.sn2;  // k(x*,x*) incl. the i==j noise term (MatrixUtils.scala:63)
             for (int i = 0; i < ms; ++i) var[(size_t)(b0 + b) * ms + i] = kss - var[(size_t)(b0 + b) * ms + i];
             if (info) info[b0 + b] = hinfo[b0 + b];
             if (hinfo[b0 + b] && !bad) { bad = 1; h->last_info = hinfo[b0 + b]; }

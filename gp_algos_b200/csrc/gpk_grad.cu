@@ -144,6 +144,58 @@ __global__ void __launch_bounds__(256) grad_trace_kernel(const GradArgs a) {
     }
 }
 
+// Co2Kernel (gp/regression/Co2Prediction.scala:66-137): same tiling and reduction, 1-D inputs, the 11 derivatives of one pair
+// share their sub-expressions (co2_derivs); partial[..][p] = sum over the tile of mult * W_ij * dk_p(x_i, x_j, i == j).
+__global__ void __launch_bounds__(256) grad_trace_co2_kernel(const GradArgs a) {
+    __shared__ double red[8];
+    __shared__ double xi[GT], xj[GT];
+    const int64_t pb = blockIdx.y;
+    const CovParams& cp = a.pp ? a.pp[pb].cp : a.cp;
+    const double* Kinv = a.Kinv ? a.Kinv + pb * (int64_t)a.N * a.N : nullptr;
+    const double* X = a.X + pb * a.strideX;
+    const double* alpha = a.alpha + pb * a.N;
+    const int t = blockIdx.x;
+    int bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    while ((int64_t)bi * (bi + 1) / 2 > t) --bi;
+    const int bj = t - (int)((int64_t)bi * (bi + 1) / 2);
+    const int i0 = bi * GT, j0 = bj * GT;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    if (tid < GT) {
+        xi[tid] = (i0 + tid < a.n) ? X[i0 + tid] : 0.0;
+        xj[tid] = (j0 + tid < a.n) ? X[j0 + tid] : 0.0;
+    }
+    __syncthreads();
+    const int gi0 = i0 + 2 * tx;
+    const double al0 = (gi0 < a.n) ? alpha[gi0] : 0.0, al1 = (gi0 + 1 < a.n) ? alpha[gi0 + 1] : 0.0;
+    double acc[GPK_CO2_NPARAMS];
+#pragma unroll
+    for (int p = 0; p < GPK_CO2_NPARAMS; ++p) acc[p] = 0.0;
+    for (int b = 0; b < 8; ++b) {
+        const int gj = j0 + ty + 8 * b;
+        const double aj = (gj < a.n) ? alpha[gj] : 0.0;
+        const double2 kv = Kinv ? *reinterpret_cast<const double2*>(Kinv + gi0 + (int64_t)gj * a.N) : make_double2(0.0, 0.0);
+        for (int q = 0; q < 2; ++q) {
+            const int gi = gi0 + q;
+            if (!(gi < a.n && gj < a.n && gi >= gj)) continue;
+            const double w = ((q ? al1 : al0) * aj - (q ? kv.y : kv.x)) * ((gi == gj) ? 1.0 : 2.0);
+            Co2Terms tm;
+            double dk[GPK_CO2_NPARAMS];
+            co2_value(cp.inv_ls2, xi[2 * tx + q] - xj[ty + 8 * b], tm);
+            co2_derivs(cp.inv_ls2, tm, dk);
+            dk[10] = (gi == gj) ? 2 * cp.inv_ls2[10] : 0.0;
+#pragma unroll
+            for (int p = 0; p < GPK_CO2_NPARAMS; ++p) acc[p] += w * dk[p];
+        }
+    }
+    double* out = a.partial + (pb * gridDim.x + blockIdx.x) * (int64_t)GPK_CO2_NPARAMS;
+#pragma unroll
+    for (int p = 0; p < GPK_CO2_NPARAMS; ++p) {
+        const double ts = block_sum(acc[p], red);
+        if (tid == 0) out[p] = ts;
+    }
+}
+
 // g[b][p] = gscale_b[p] * sum_blocks partial[b][block][p]   (fixed order -> deterministic)
 struct GradScale { double s[GPK_MAX_D + 2]; };
 __global__ void __launch_bounds__(256) grad_finish_kernel(const double* partial, int nblocks, int np_all, int nparams,
@@ -169,14 +221,16 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(const double* partial,
 
 size_t gpk_grad_scratch_doubles(int N, int D) {
     const size_t tiles = (size_t)(N / GT) * (N / GT + 1) / 2;
-    return tiles * (D + 2) + (D + 2);
+    const size_t np = (size_t)(D + 2 > GPK_CO2_NPARAMS ? D + 2 : GPK_CO2_NPARAMS);   // either kernel family
+    return tiles * np + np;
 }
 
 int gpk_grad_trace(gpk_handle h, const double* Kinv, int N, const double* dX, int n, int64_t ldx, const double* alpha,
                    const ProblemParams& pp, int nparams, double* g_out, double* scratch, int batch, int64_t strideX,
                    const ProblemParams* pp_dev, int64_t strideOut) {
     const int D = pp.cp.D;
-    if (nparams < 0 || nparams > D + 2) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, D + 2);
+    const int np_all = pp.cp.kind == GPK_KERNEL_CO2 ? GPK_CO2_NPARAMS : D + 2;
+    if (nparams < 0 || nparams > np_all) return gpk_set_error(h, GPK_EINVAL, "nparams=%d outside 0..%d", nparams, np_all);
     if (nparams == 0) return GPK_OK;
     const int nt = (n + GT - 1) / GT;
     const int nblocks = nt * (nt + 1) / 2;
@@ -188,11 +242,12 @@ int gpk_grad_trace(gpk_handle h, const double* Kinv, int N, const double* dX, in
         GPK_CUDA(h, cudaFuncSetAttribute(grad_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->func_cfg |= (1u << 9);
     }
-    grad_trace_kernel<<<dim3(nblocks, batch), 256, smem, h->stream>>>(a);
+    if (pp.cp.kind == GPK_KERNEL_CO2) grad_trace_co2_kernel<<<dim3(nblocks, batch), 256, 0, h->stream>>>(a);
+    else grad_trace_kernel<<<dim3(nblocks, batch), 256, smem, h->stream>>>(a);
     GPK_LAUNCH_CHECK(h);
     GradScale sc;
     memcpy(sc.s, pp.gscale, sizeof(sc.s));
-    grad_finish_kernel<<<dim3(nparams, batch), 256, 0, h->stream>>>(scratch, nblocks, D + 2, nparams, sc, pp_dev, g_out, strideOut);
+    grad_finish_kernel<<<dim3(nparams, batch), 256, 0, h->stream>>>(scratch, nblocks, np_all, nparams, sc, pp_dev, g_out, strideOut);
     GPK_LAUNCH_CHECK(h);
     return GPK_OK;
 }

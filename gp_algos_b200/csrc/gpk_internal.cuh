@@ -39,6 +39,7 @@ struct gpk_handle_s {
     struct gpk_eval_graph* eval_graph;
     struct gpk_capture_log* cap;  // non-null while capturing: every kernel node with the priority of the stream it came from
     int prio_main, prio_side, prio_pipe;
+    int kernel_family;            // gpk_kernel_family: how (D, theta) arguments are interpreted
     char err[512];
 };
 void gpk_capture_note(gpk_handle h);    // gpk_gp.cu
@@ -113,13 +114,56 @@ int gpk_gemm(gpk_handle h, const GemmDesc& g);
 // batch == 1 and pp_dev == nullptr the hyper-parameters travel by value in the kernel arguments.
 // ---------------------------------------------------------------------------------------------
 #define GPK_MAX_D 64
+#define GPK_CO2_NPARAMS 11
 struct CovParams {
     int D;
-    double sf2;          // signalVar*signalVar
-    double sn2;          // noiseVar*noiseVar
+    int kind;            // gpk_kernel_family
+    double sf2;          // SE-ARD: signalVar*signalVar.          Co2: k(x,x) without noise = hp1^2 + hp3^2 + hp6^2 + hp9^2
+    double sn2;          // SE-ARD: noiseVar*noiseVar.            Co2: hp11^2
     double extra_diag;   // Option sigmaNoise (un-squared), 0 when None
-    double inv_ls2[GPK_MAX_D];  // 1/(ls*ls)
+    double inv_ls2[GPK_MAX_D];  // SE-ARD: 1/(ls*ls).             Co2: hp1..hp11, then pow(hp2,-3), pow(hp4,-3), pow(hp5,-3), pow(hp7,-3), pow(hp10,-3)
 };
+static inline int gpk_theta_len(const gpk_handle_s* h, int D) { return h->kernel_family == GPK_KERNEL_CO2 ? GPK_CO2_NPARAMS : D + 2; }
+
+#ifdef __CUDACC__
+// gp/regression/Co2Prediction.scala:38-56 (apply) and :66-137 (derAfterHyperParam) on one pair of 1-D inputs, xd = x1 - x2.
+// Products and sums keep the Scala evaluation order; intrinsics keep nvcc from contracting a*b+c into an fma where the JVM
+// rounds twice.  par = CovParams::inv_ls2 of the Co2 family.
+struct Co2Terms { double sq, s, e1, k2, p1, pw, k4; };
+__device__ __forceinline__ double co2_value(const double* __restrict__ par, double xd, Co2Terms& t) {
+    const double hp1 = par[0], hp2 = par[1], hp3 = par[2], hp4 = par[3], hp5 = par[4], hp6 = par[5], hp7 = par[6], hp8 = par[7],
+                 hp9 = par[8], hp10 = par[9];
+    t.sq = __dmul_rn(xd, xd);
+    t.e1 = exp(-t.sq / __dmul_rn(__dmul_rn(2.0, hp2), hp2));
+    t.s = sin(__dmul_rn(3.14159265358979323846, xd));
+    const double a2 = -t.sq / __dmul_rn(__dmul_rn(2.0, hp4), hp4);
+    const double b2 = __dmul_rn(__dmul_rn(2.0, t.s), t.s) / __dmul_rn(hp5, hp5);
+    t.k2 = __dmul_rn(__dmul_rn(hp3, hp3), exp(__dsub_rn(a2, b2)));
+    t.p1 = __dadd_rn(1.0, t.sq / __dmul_rn(__dmul_rn(__dmul_rn(2.0, hp8), hp7), hp7));
+    t.pw = pow(t.p1, -hp8);
+    t.k4 = __dmul_rn(__dmul_rn(hp9, hp9), exp(-t.sq / __dmul_rn(__dmul_rn(2.0, hp10), hp10)));
+    const double k1 = __dmul_rn(__dmul_rn(hp1, hp1), t.e1), k3 = __dmul_rn(__dmul_rn(hp6, hp6), t.pw);
+    return __dadd_rn(__dadd_rn(__dadd_rn(k1, t.k2), k3), t.k4);
+}
+// dk/dhp_p for p = 1..10 (0-based slot p-1) from the shared sub-expressions; p = 11 is 2 hp11 [i == j] and handled by the callers
+__device__ __forceinline__ void co2_derivs(const double* __restrict__ par, const Co2Terms& t, double* __restrict__ dk) {
+    const double hp1 = par[0], hp3 = par[2], hp6 = par[5], hp7 = par[6], hp8 = par[7], hp9 = par[8];
+    dk[0] = __dmul_rn(__dmul_rn(2.0, hp1), t.e1);
+    dk[1] = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(hp1, hp1), t.e1), t.sq), par[11]);
+    dk[2] = __dmul_rn(2.0, t.k2) / hp3;
+    dk[3] = __dmul_rn(__dmul_rn(t.k2, t.sq), par[12]);
+    dk[4] = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(t.k2, 4.0), t.s), t.s), par[13]);
+    dk[5] = __dmul_rn(__dmul_rn(2.0, hp6), t.pw);
+    dk[6] = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(hp6, hp6), pow(t.p1, __dsub_rn(-hp8, 1.0))), t.sq), par[14]);
+    const double lg = log(t.p1);
+    const double first = exp(__dmul_rn(-hp8, lg));
+    const double den = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, hp7), hp7), hp8), hp8), t.p1);
+    const double second = __dadd_rn(-lg, __dmul_rn(hp8, t.sq) / den);
+    dk[7] = __dmul_rn(__dmul_rn(__dmul_rn(hp6, hp6), first), second);
+    dk[8] = __dmul_rn(2.0, t.k4) / hp9;
+    dk[9] = __dmul_rn(__dmul_rn(t.k4, t.sq), par[15]);
+}
+#endif
 struct ProblemParams {
     CovParams cp;
     double gscale[GPK_MAX_D + 2];  // 1/2 * {2 sf, sf^2 / l_d^3 ..., 2 sn}: factors of the gradient trace

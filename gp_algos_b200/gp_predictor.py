@@ -8,6 +8,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
+from .co2_prediction import Co2HyperParams, Co2Kernel
 from .kernel_requisites import GaussianRbfKernel, GaussianRbfParams
 
 
@@ -44,7 +45,7 @@ class PredictionInput:
 
 
 def _theta_of(hyperParams) -> np.ndarray:
-    if isinstance(hyperParams, GaussianRbfParams):
+    if isinstance(hyperParams, (GaussianRbfParams, Co2HyperParams)):
         return np.ascontiguousarray(hyperParams.toDenseVector)
     return np.ascontiguousarray(np.asarray(hyperParams, dtype=np.float64))
 
@@ -53,11 +54,27 @@ class GpPredictor:
     """GpPredictor.scala:15: constructed from a kernel function (same one-argument constructor the Spring
     beans use, spring-context.xml:33-51)."""
 
-    def __init__(self, kernelFunc: GaussianRbfKernel, handle: _lib.Handle | None = None):
-        if not isinstance(kernelFunc, GaussianRbfKernel):
-            raise TypeError("only GaussianRbfKernel is lowered to the GPU path")
+    def __init__(self, kernelFunc, handle: _lib.Handle | None = None):
+        if not isinstance(kernelFunc, (GaussianRbfKernel, Co2Kernel)):
+            raise TypeError("only GaussianRbfKernel and Co2Kernel are lowered to the GPU path")
         self.kernelFunc = kernelFunc
         self._handle = handle
+
+    def _theta(self, hyperParams, D: int) -> np.ndarray:
+        """theta as libgpk reads it for this predictor's kernel family, with the reference's own failure modes."""
+        theta = _theta_of(hyperParams if hyperParams is not None else self.kernelFunc.hyperParams)
+        if isinstance(self.kernelFunc, Co2Kernel):
+            if D != 1:       # require(...) Co2Prediction.scala:39
+                raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, "requirement failed: This kernel is applicable only for 1D objects")
+            if len(theta) < 11:   # getHyperParams reads positions 1..11 (Co2Prediction.scala:87-92)
+                raise IndexError(f"java.lang.IndexOutOfBoundsException: {len(theta)} not in [0,{len(theta)})")
+            return np.ascontiguousarray(theta[:11])
+        if len(theta) != D + 2:   # require(...) KernelRequisites.scala:55
+            raise ValueError(f"requirement failed: {len(theta)} does not equal to {D + 2}")
+        return theta
+
+    def _family(self):
+        return self.handle.kernel_family(self.kernelFunc.family)
 
     @property
     def handle(self) -> _lib.Handle:
@@ -79,48 +96,47 @@ class GpPredictor:
         """-> (L, alphaVec, Option[noise * I]).  Like the reference, the third element is a dense n x n matrix
         when sigmaNoise is defined (GpPredictor.scala:116-117); it is built lazily on the host."""
         h = self.handle
-        theta = _theta_of(hyperParams if hyperParams is not None else self.kernelFunc.hyperParams)
         X, y = self._xy(trainingData, targets)
         n, D = X.shape
-        if len(theta) != D + 2:
-            raise ValueError(f"requirement failed: {len(theta)} does not equal to {D + 2}")
+        theta = self._theta(hyperParams, D)
         L = np.empty((n, n), order="F")
         alpha = np.empty(n)
         ll = C.c_double()
-        h.check(h.lib.gpk_gp_fit(h.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(theta), int(sigmaNoise is not None),
-                                 float(sigmaNoise or 0.0), _lib.ptr(L), n, _lib.ptr(alpha), C.addressof(ll)))
+        with self._family():
+            h.check(h.lib.gpk_gp_fit(h.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(theta), int(sigmaNoise is not None),
+                                     float(sigmaNoise or 0.0), _lib.ptr(L), n, _lib.ptr(alpha), C.addressof(ll)))
         noise = None if sigmaNoise is None else np.eye(n) * sigmaNoise
         return L, alpha, noise
 
     # ---- GpPredictor.scala:60-80 ----------------------------------------------------------------------
     def logLikelihoodWithDerivatives(self, input: PredictionTrainingInput, hyperParams, optimizedParamsNum: int):
         h = self.handle
-        theta = _theta_of(hyperParams)
         X, y = self._xy(input.trainingData, input.targets)
         n, D = X.shape
-        if len(theta) != D + 2:
-            raise ValueError(f"requirement failed: {len(theta)} does not equal to {D + 2}")
+        theta = self._theta(hyperParams, D)
         ll = C.c_double()
         g = np.zeros(max(optimizedParamsNum, 1))
         s = input.sigmaNoise
-        h.check(h.lib.gpk_gp_nll_grad(h.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(theta), int(s is not None),
-                                      float(s or 0.0), int(optimizedParamsNum), C.addressof(ll), _lib.ptr(g)))
+        with self._family():
+            h.check(h.lib.gpk_gp_nll_grad(h.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(theta), int(s is not None),
+                                          float(s or 0.0), int(optimizedParamsNum), C.addressof(ll), _lib.ptr(g)))
         return ll.value, g[:optimizedParamsNum]
 
     # ---- GpPredictor.scala:24-43 ----------------------------------------------------------------------
     def predict(self, input: PredictionInput, hyperParams=None):
         h = self.handle
-        theta = _theta_of(hyperParams if hyperParams is not None else self.kernelFunc.hyperParams)
         X, y = self._xy(input.trainingData, input.targets)
         Xs = _lib.fmat(input.testData)
         n, D = X.shape
+        theta = self._theta(hyperParams, D)
         m = Xs.shape[0]
         mean = np.empty(m)
         sigma = np.empty((m, m), order="F")
         ll = C.c_double()
         s = input.sigmaNoise
-        h.check(h.lib.gpk_gp_predict(h.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(Xs), m, m, _lib.ptr(theta),
-                                     int(s is not None), float(s or 0.0), _lib.ptr(mean), _lib.ptr(sigma), m, C.addressof(ll)))
+        with self._family():
+            h.check(h.lib.gpk_gp_predict(h.h, _lib.ptr(X), n, D, n, _lib.ptr(y), _lib.ptr(Xs), m, m, _lib.ptr(theta),
+                                         int(s is not None), float(s or 0.0), _lib.ptr(mean), _lib.ptr(sigma), m, C.addressof(ll)))
         return GaussianDistribution(mean, sigma), ll.value
 
     # ---- GpPredictor.scala:126-142 ---------------------------------------------------------------------
@@ -159,7 +175,8 @@ class GpPredictor:
         """-> (GaussianDistribution(mean, sigma), vMatrix).  The factor `l` is adopted on the device
         (its inverse is formed once) -- use FittedGp for the fit-once / predict-many pattern."""
         kf = kernelFunc or self.kernelFunc
-        model = FittedGp.from_factor(self.handle, trainingData, l, alphaVec, kf)
+        with self.handle.kernel_family(kf.family):
+            model = FittedGp.from_factor(self.handle, trainingData, l, alphaVec, kf)
         try:
             return model.computePosterior(testData)
         finally:
@@ -168,8 +185,9 @@ class GpPredictor:
     def fit(self, trainingData, sigmaNoise, targets, hyperParams=None) -> "FittedGp":
         """Device-resident preComputeComponents: the GP-UKF / GP-UCB call pattern
         (GPUnscentedKalmanFilter.scala:77-88,123-147) without moving L across PCIe."""
-        theta = _theta_of(hyperParams if hyperParams is not None else self.kernelFunc.hyperParams)
-        return FittedGp.fit(self.handle, trainingData, targets, theta, sigmaNoise)
+        theta = self._theta(hyperParams, _lib.fmat(trainingData).shape[1])
+        with self._family():
+            return FittedGp.fit(self.handle, trainingData, targets, theta, sigmaNoise)
 
 
 def models_mean(models, testData) -> np.ndarray:

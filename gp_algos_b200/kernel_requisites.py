@@ -53,6 +53,8 @@ class GaussianRbfKernel:
     """KernelRequisites.scala:62-114: k(x,x') = sf^2 exp(-1/2 (x-x')^t diag(l^-2) (x-x')) + sn^2 [p==q]."""
     rbfParams: GaussianRbfParams
 
+    family = 0   # GPK_KERNEL_SE_ARD (include/gpk.h)
+
     @property
     def hyperParametersNum(self) -> int:
         return len(self.rbfParams.lengthScales) + 2

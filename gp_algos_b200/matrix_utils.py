@@ -1,8 +1,8 @@
 """Host mirror of utils/MatrixUtils.scala: same function names and argument meaning, NumPy arrays
 (column-major copies are made as needed) instead of Breeze DenseMatrix/DenseVector, CUDA underneath.
 
-Only `GaussianRbfKernel` can be lowered to the GPU; any other kernel object is
-rejected with TypeError -- a Scala shim would leave those on the original JVM path."""
+Only the closed-form kernels `GaussianRbfKernel` and `Co2Kernel` are lowered to the GPU; any other kernel
+object is rejected with TypeError -- a Scala shim would leave those on the original JVM path."""
 from __future__ import annotations
 
 import ctypes as C
@@ -10,12 +10,13 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
+from .co2_prediction import Co2Kernel
 from .kernel_requisites import GaussianRbfKernel
 
 
 def _need_rbf(kernelFun):
-    if not isinstance(kernelFun, GaussianRbfKernel):
-        raise TypeError("only GaussianRbfKernel is lowered to the GPU path")
+    if not isinstance(kernelFun, (GaussianRbfKernel, Co2Kernel)):
+        raise TypeError("only GaussianRbfKernel and Co2Kernel are lowered to the GPU path")
     return np.ascontiguousarray(kernelFun.theta)
 
 
@@ -27,14 +28,16 @@ def buildKernelMatrix(kernelFun, input1, input2=None, handle=None) -> np.ndarray
     n, D = X1.shape
     if input2 is None:
         K = np.empty((n, n), order="F")
-        h.check(h.lib.gpk_cov_se_ard(h.h, _lib.ptr(X1), n, D, n, _lib.ptr(theta), _lib.ptr(K), n))
+        with h.kernel_family(kernelFun.family):
+            h.check(h.lib.gpk_cov_se_ard(h.h, _lib.ptr(X1), n, D, n, _lib.ptr(theta), _lib.ptr(K), n))
         return K
     X2 = _lib.fmat(input2)
     m = X2.shape[0]
     if X2.shape[1] != D:
         raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, "feature dimensions differ")
     K = np.empty((n, m), order="F")
-    h.check(h.lib.gpk_cov_cross_se_ard(h.h, _lib.ptr(X1), n, n, _lib.ptr(X2), m, m, D, _lib.ptr(theta), _lib.ptr(K), max(n, 1)))
+    with h.kernel_family(kernelFun.family):
+        h.check(h.lib.gpk_cov_cross_se_ard(h.h, _lib.ptr(X1), n, n, _lib.ptr(X2), m, m, D, _lib.ptr(theta), _lib.ptr(K), max(n, 1)))
     return K
 
 
@@ -44,10 +47,11 @@ def buildKernelDerMatrix(kernelFun, data, paramNum: int, handle=None) -> np.ndar
     theta = _need_rbf(kernelFun)
     X = _lib.fmat(data)
     n, D = X.shape
-    if not 1 <= paramNum <= D + 2:
+    if not 1 <= paramNum <= kernelFun.hyperParametersNum:
         raise LookupError(f"scala.MatchError: {paramNum}")
     dK = np.empty((n, n), order="F")
-    h.check(h.lib.gpk_cov_deriv_se_ard(h.h, int(paramNum), _lib.ptr(X), n, D, n, _lib.ptr(theta), _lib.ptr(dK), n))
+    with h.kernel_family(kernelFun.family):
+        h.check(h.lib.gpk_cov_deriv_se_ard(h.h, int(paramNum), _lib.ptr(X), n, D, n, _lib.ptr(theta), _lib.ptr(dK), n))
     return dK
 
 

@@ -57,6 +57,22 @@ const char* gpk_version(void);
  * (default 1, or the GPK_GRAPH environment variable).  Results are identical either way. */
 int gpk_set_graph_mode(gpk_handle h, int on);
 
+/* ---- kernel family -------------------------------------------------------------------------------
+ * The reference's GpPredictor works on any utils.KernelRequisites.KernelFunc; two of them are closed-form and are lowered
+ * to the device.  The family is a property of the handle and applies to every later call that takes (D, theta):
+ *   GPK_KERNEL_SE_ARD  GaussianRbfKernel, utils/KernelRequisites.scala:62-114: theta = [signalVar, lengthScale_1..D, noiseVar]
+ *   GPK_KERNEL_CO2     Co2Kernel, gp/regression/Co2Prediction.scala:29-137: 1-D inputs (D must be 1), theta = hp1..hp11,
+ *                      k = hp1^2 exp(-r^2/(2 hp2^2)) + hp3^2 exp(-r^2/(2 hp4^2) - 2 sin^2(pi r)/hp5^2)
+ *                        + hp6^2 (1 + r^2/(2 hp8 hp7^2))^-hp8 + hp9^2 exp(-r^2/(2 hp10^2)) + hp11^2 [i == j]
+ *                      with the derivatives of :66-137; `gradient` is `???` in the reference -> gpk_gp_model_ucb: GPK_EINVAL.
+ * A resident model (gpk_model) keeps the family it was fitted with.  The Scala shim selects the family by pattern-matching
+ * on the KernelFunc class; other kernels (PMKKernel) stay on the Scala path. */
+enum gpk_kernel_family { GPK_KERNEL_SE_ARD = 0, GPK_KERNEL_CO2 = 1 };
+int gpk_set_kernel_family(gpk_handle h, int family);
+int gpk_get_kernel_family(gpk_handle h);
+/* number of hyper-parameters (length of theta) of the handle's family for D-dimensional inputs: D + 2, or 11 */
+int gpk_theta_length(gpk_handle h, int D);
+
 /* ---- fine-grained MatrixUtils replacements ---------------------------------------------------- */
 /* utils/MatrixUtils.scala:57-70  buildKernelMatrix(kernel, data): symmetric n x n,
  * K(i,j) = sf^2 exp(-1/2 sum_d (x_id-x_jd)^2/l_d^2) + sn^2 [i==j]; lower triangle computed, mirrored. */

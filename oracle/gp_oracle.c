@@ -83,16 +83,80 @@ void orc_rbf_grad_x(int after_first_arg, const double *x1, long inc1, const doub
     }
 }
 
+
+/* ---- gp/regression/Co2Prediction.scala:29-137  Co2Kernel (1-D inputs, 11 hyper-parameters) ----------
+ * The reference's second KernelFunc (R&W's Mauna Loa kernel); it flows through the same GpPredictor code
+ * (changeHyperParams / apply / derAfterHyperParam).  hp[0..10] = hp1..hp11 (getAtPosition is 1-based, :23).
+ * Expressions keep the Scala evaluation order (left-associative products and sums).  breeze.numerics
+ * exp/sin/pow are java.lang.Math on doubles -> libm here.
+ * Kernel family switch: orc_set_kernel(0) = GaussianRbfKernel (theta = [sf, ls.., sn], D+2 entries),
+ * orc_set_kernel(1) = Co2Kernel (theta = hp1..hp11, D must be 1).  The matrix builders below dispatch on it,
+ * so every GpPredictor-level routine of this file serves both kernels, like the Scala class does. */
+static int orc_kernel_kind = 0;
+void orc_set_kernel(int kind) { orc_kernel_kind = kind; }
+int orc_get_kernel(void) { return orc_kernel_kind; }
+
+/* Co2Prediction.scala:38-56 apply */
+double orc_co2_k(double x1, double x2, const double *hp, int same_index)
+{
+    double hp1 = hp[0], hp2 = hp[1], hp3 = hp[2], hp4 = hp[3], hp5 = hp[4], hp6 = hp[5], hp7 = hp[6],
+           hp8 = hp[7], hp9 = hp[8], hp10 = hp[9], hp11 = hp[10];
+    double xDiff = x1 - x2, xDiffSq = (x1 - x2) * (x1 - x2);
+    double k1Val = hp1 * hp1 * exp(-xDiffSq / (2 * hp2 * hp2));
+    double sinVal = sin(M_PI * xDiff);
+    double k2Val = hp3 * hp3 * exp((-xDiffSq / (2 * hp4 * hp4)) - 2 * sinVal * sinVal / (hp5 * hp5));
+    double k3Pow1 = 1 + xDiffSq / (2 * hp8 * hp7 * hp7);
+    double k3Val = hp6 * hp6 * pow(k3Pow1, -hp8);
+    double k4Val = hp9 * hp9 * exp(-xDiffSq / (2 * hp10 * hp10));
+    double indNoise = same_index ? hp11 * hp11 : 0.;
+    return k1Val + k2Val + k3Val + k4Val + indNoise;
+}
+
+/* Co2Prediction.scala:66-137 derAfterHyperParam (param_num 1-based; outside 1..11 is a scala.MatchError -> NAN) */
+double orc_co2_dk(int param_num, double x1, double x2, const double *hp, int same_index)
+{
+    double hp1 = hp[0], hp2 = hp[1], hp3 = hp[2], hp4 = hp[3], hp5 = hp[4], hp6 = hp[5], hp7 = hp[6],
+           hp8 = hp[7], hp9 = hp[8], hp10 = hp[9], hp11 = hp[10];
+    double xDiff = x1 - x2, sqDiff = (x1 - x2) * (x1 - x2);
+    if (param_num < 1 || param_num > 11) return NAN;
+    if (param_num < 3) {                                             /* derAfterFirstKernel :93-99 */
+        if (param_num == 1) return 2 * hp1 * exp(-sqDiff / (2 * hp2 * hp2));
+        return hp1 * hp1 * exp(-sqDiff / (2 * hp2 * hp2)) * sqDiff * pow(hp2, -3);
+    }
+    if (param_num < 6) {                                             /* derAfterSecondKernel :101-110 */
+        double sinVal = sin(M_PI * xDiff);
+        double k2Val = hp3 * hp3 * exp(-sqDiff / (2 * hp4 * hp4) - 2 * sinVal * sinVal / (hp5 * hp5));
+        if (param_num == 3) return 2 * k2Val / hp3;
+        if (param_num == 4) return k2Val * sqDiff * pow(hp4, -3);
+        return k2Val * 4 * sinVal * sinVal * pow(hp5, -3);
+    }
+    if (param_num < 9) {                                             /* derAfterThirdKernel :112-123 */
+        double k3Pow1 = 1 + sqDiff / (2 * hp8 * hp7 * hp7);
+        if (param_num == 6) return 2 * hp6 * pow(k3Pow1, -hp8);
+        if (param_num == 7) return hp6 * hp6 * pow(k3Pow1, -hp8 - 1) * sqDiff * pow(hp7, -3);
+        double firstTerm = exp(-hp8 * log(k3Pow1));
+        double secondTerm = -log(k3Pow1) + (hp8 * sqDiff / (2 * hp7 * hp7 * hp8 * hp8 * k3Pow1));
+        return hp6 * hp6 * firstTerm * secondTerm;
+    }
+    {                                                                /* derAfterFourthKernel :125-135 */
+        double k4Val = hp9 * hp9 * exp(-sqDiff / (2 * hp10 * hp10));
+        if (param_num == 9) return 2 * k4Val / hp9;
+        if (param_num == 10) return k4Val * sqDiff * pow(hp10, -3);
+        return same_index ? 2 * hp11 : 0.;
+    }
+}
+
 /* ---- utils/MatrixUtils.scala:57-70  buildKernelMatrix(kernel,data) ---------------------- */
 /* theta = [sf, ls_1..ls_D, sn] (KernelRequisites.scala:39-58). X is n x D column-major. */
 void orc_build_kernel_matrix(const double *X, int n, int D, long ldx, const double *theta,
                              double *K, long ldk)
 {
-    double sf = theta[0], sn = theta[D + 1];
+    double sf = theta[0], sn = orc_kernel_kind ? 0.0 : theta[D + 1];
     const double *ls = theta + 1;
     for (int i = 0; i < n; ++i)
         for (int j = 0; j <= i; ++j) {
-            double v = orc_rbf_k(X + i, ldx, X + j, ldx, D, sf, ls, sn, i == j);
+            double v = orc_kernel_kind ? orc_co2_k(X[i], X[j], theta, i == j)
+                                       : orc_rbf_k(X + i, ldx, X + j, ldx, D, sf, ls, sn, i == j);
             K[i + (long)j * ldk] = v;
             K[j + (long)i * ldk] = v;
         }
@@ -102,22 +166,24 @@ void orc_build_kernel_matrix(const double *X, int n, int D, long ldx, const doub
 void orc_build_kernel_matrix_cross(const double *X1, int m, long ldx1, const double *X2, int n,
                                    long ldx2, int D, const double *theta, double *K, long ldk)
 {
-    double sf = theta[0], sn = theta[D + 1];
+    double sf = theta[0], sn = orc_kernel_kind ? 0.0 : theta[D + 1];
     const double *ls = theta + 1;
     for (int i = 0; i < m; ++i)
         for (int j = 0; j < n; ++j)
-            K[i + (long)j * ldk] = orc_rbf_k(X1 + i, ldx1, X2 + j, ldx2, D, sf, ls, sn, 0);
+            K[i + (long)j * ldk] = orc_kernel_kind ? orc_co2_k(X1[i], X2[j], theta, 0)
+                                                   : orc_rbf_k(X1 + i, ldx1, X2 + j, ldx2, D, sf, ls, sn, 0);
 }
 
 /* ---- utils/MatrixUtils.scala:72-84 with f = derAfterHyperParam(p) (GpPredictor.scala:72-75) */
 void orc_build_der_matrix(int param_num, const double *X, int n, int D, long ldx,
                           const double *theta, double *dK, long ldk)
 {
-    double sf = theta[0], sn = theta[D + 1];
+    double sf = theta[0], sn = orc_kernel_kind ? 0.0 : theta[D + 1];
     const double *ls = theta + 1;
     for (int i = 0; i < n; ++i)
         for (int j = 0; j <= i; ++j) {
-            double v = orc_rbf_dk(param_num, X + i, ldx, X + j, ldx, D, sf, ls, sn, i == j);
+            double v = orc_kernel_kind ? orc_co2_dk(param_num, X[i], X[j], theta, i == j)
+                                       : orc_rbf_dk(param_num, X + i, ldx, X + j, ldx, D, sf, ls, sn, i == j);
             dK[i + (long)j * ldk] = v;
             dK[j + (long)i * ldk] = v;
         }

@@ -58,6 +58,10 @@ def _L():
         _lib.orc_dnorm.restype = C.c_double
         _lib.orc_ep_avg_between.restype = C.c_double
         _lib.orc_ep_marginal_likelihood.restype = C.c_double
+        _lib.orc_co2_k.restype = C.c_double
+        _lib.orc_co2_k.argtypes = [C.c_double, C.c_double, _dp, C.c_int]
+        _lib.orc_co2_dk.restype = C.c_double
+        _lib.orc_co2_dk.argtypes = [C.c_int, C.c_double, C.c_double, _dp, C.c_int]
     return _lib
 
 
@@ -108,6 +112,68 @@ def get_at_position(theta, i):
     if i == D + 2:
         return theta[D + 1]
     raise LookupError("scala.MatchError")
+
+
+# --------------------------------------------------------------------------------------------
+# Co2Kernel (gp/regression/Co2Prediction.scala:29-137): the reference's second KernelFunc.  theta = hp1..hp11, 1-D inputs.
+# `with co2_kernel():` switches every lit_* routine below to it (the C builders dispatch on the family, like GpPredictor
+# dispatches on its kernelFunc).
+# --------------------------------------------------------------------------------------------
+KERNEL_SE_ARD, KERNEL_CO2 = 0, 1
+CO2_SHIPPED_HP = np.array([60., 70., 8., 50., 2., 0.34, 2.4, 0.88, 0.26, 0.2, 0.19])   # utils/TestingUtils.scala:17-20
+
+
+class co2_kernel:
+    def __enter__(self):
+        self.prev = _L().orc_get_kernel()
+        _L().orc_set_kernel(KERNEL_CO2)
+        return self
+
+    def __exit__(self, *exc):
+        _L().orc_set_kernel(self.prev)
+        return False
+
+
+def co2_k(x1, x2, hp, same_index=False):
+    """Co2Prediction.scala:38-56 apply."""
+    hp = np.ascontiguousarray(hp, dtype=np.float64)
+    assert hp.size == 11
+    return _L().orc_co2_k(float(x1), float(x2), _p(hp), int(same_index))
+
+
+def co2_dk(param_num, x1, x2, hp, same_index=False):
+    """Co2Prediction.scala:66-137 derAfterHyperParam(param_num), 1-based."""
+    hp = np.ascontiguousarray(hp, dtype=np.float64)
+    assert hp.size == 11
+    v = _L().orc_co2_dk(int(param_num), float(x1), float(x2), _p(hp), int(same_index))
+    if math.isnan(v) and not 1 <= param_num <= 11:
+        raise LookupError("scala.MatchError")
+    return v
+
+
+def co2_data_to_year_with_value(matrix, train_test_ratio):
+    """Co2Prediction.scala:159-186 co2DataToYearWithValue: rows (year, 12 monthly ppm, annual mean) -> (year + (month-1)/12, ppm)
+    for ppm > 0, split by ratio (trainNum = (rows * ratio).toInt)."""
+    if not 0 <= train_test_ratio <= 1:
+        raise ValueError("requirement failed: Division's ratio should be between 0 and 1")
+    rows = []
+    for r in range(matrix.shape[0]):
+        year = matrix[r, 0]
+        for month in range(1, matrix.shape[1] - 1):
+            if matrix[r, month] > 0:
+                rows.append((year + (1 / 12.) * (month - 1), matrix[r, month]))
+    whole = np.array(rows, dtype=np.float64)
+    train_num = int(whole.shape[0] * train_test_ratio)
+    return whole[:train_num], whole[train_num:]
+
+
+def make_co2_like(n=400, seed=9, years=(1958.0, 1992.0)):
+    """Synthetic stand-in for the Mauna Loa series (the GPU box cannot read /root/reference): monthly-ish samples of a trend
+    + annual cycle + noise on the same time axis and ppm scale, hyper-parameters = the shipped ones."""
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(years[0], years[1], size=n))
+    y = 315.0 + 1.3 * (t - years[0]) + 0.012 * (t - years[0]) ** 2 + 3.0 * np.sin(2 * np.pi * t) + 0.2 * rng.standard_normal(n)
+    return t.reshape(n, 1), y, CO2_SHIPPED_HP.copy()
 
 
 # --------------------------------------------------------------------------------------------
@@ -215,7 +281,7 @@ def lit_loglik_with_derivs(X, y, theta, sigma_noise=None, nparams=None):
     y = np.ascontiguousarray(y, dtype=np.float64)
     theta = np.ascontiguousarray(theta, dtype=np.float64)
     n, D = X.shape
-    nparams = D + 2 if nparams is None else nparams
+    nparams = len(theta) if nparams is None else nparams       # D + 2 (GaussianRbfKernel) or 11 (Co2Kernel)
     ll = C.c_double()
     g = np.zeros(nparams)
     _check(_L().orc_gp_loglik_with_derivs(_p(X), n, D, C.c_long(n), _p(y), _p(theta),

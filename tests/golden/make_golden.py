@@ -8,6 +8,9 @@
 * c1_small.npz, c2_small.npz, c3_small.npz, c3_grad_small.npz, c4_small.npz
                     -- reduced-size instances of BASELINE.json configs 1-4 (SURVEY.md 8(d) generators and seeds)
                        evaluated by the LITERAL oracle (oracle/gp_oracle.c).
+* co2_maunaloa.npz  -- the Co2Kernel path (gp/regression/Co2Prediction.scala) on the reference's src/main/resources/co2/maunaLoa.txt:
+                       literal-oracle outputs at the shipped hyper-parameters + the reference's shipped co2/co2PredResults.txt
+                       as a soft fixture (see co2_maunaloa below).
 * boston_soft.npz   -- soft fixture: the reference's own shipped resources src/main/resources/boston.csv and
                        src/main/resources/boston/bostonPredResults.txt (506 rows: idx, mean, sqrt(var), target; written by
                        gp/tasks/MasterThesisRelatedTasks.scala:105-122) with the hyper-parameters of
@@ -115,8 +118,37 @@ def boston_soft():
              ref_target=res[:, 3], oracle_mean=mean, oracle_std=std, oracle_ll=ll)
 
 
+def co2_maunaloa():
+    """The reference's Co2Kernel path on its own Mauna Loa data (gp/tasks/MasterThesisRelatedTasks.scala:59-71
+    evaluateGpPredictionOnCo2Ds: first 70 % of the monthly series as training set, posterior over the whole series).
+    Hard part: literal-oracle outputs at the SHIPPED hyper-parameters (utils/TestingUtils.scala:17-20).  Soft part: the
+    reference's shipped output co2/co2PredResults.txt (year, mean, sqrt(var)), written AFTER its own 20-iteration L-BFGS run
+    whose end point was only printed -- it pins the time axis exactly and the training-range posterior to ~0.15 ppm."""
+    raw = np.loadtxt(os.path.join(REF, "co2", "maunaLoa.txt"))
+    res = np.loadtxt(os.path.join(REF, "co2", "co2PredResults.txt"))
+    train, test = orc.co2_data_to_year_with_value(raw, 0.7)
+    whole = np.vstack([train, test])
+    hp = orc.CO2_SHIPPED_HP.copy()
+    X, y, Xs = train[:, :1], train[:, 1], whole[:, :1]
+    with orc.co2_kernel():
+        mean, sigma, ll = orc.lit_predict(X, y, Xs, hp, None)
+        ll2, grad = orc.lit_loglik_with_derivs(X, y, hp, None)
+        ll_s, grad_s = orc.lit_loglik_with_derivs(X, y, hp, 0.05, 7)
+        K = orc.lit_build_kernel_matrix(X, hp)
+        L, alpha = orc.lit_precompute(X, y, hp, None)
+    std = np.sqrt(np.diag(sigma))
+    nt = train.shape[0]
+    print("co2: n", nt, "ll", ll, "cond(K)", np.linalg.cond(K), "train-range max|mean - shipped|", np.abs(mean[:nt] - res[:nt, 1]).max(),
+          "max|std - shipped|", np.abs(std[:nt] - res[:nt, 2]).max(), "time axis", np.abs(whole[:, 0] - res[:, 0]).max())
+    assert ll == ll2
+    np.savez(os.path.join(HERE, "co2_maunaloa.npz"), raw_head=raw[:3], train=train, test=test, theta=hp, ll=ll, grad=grad,
+             sigma_noise=0.05, ll_s=ll_s, grad_s=grad_s, mean=mean, var=np.diag(sigma).copy(), alpha=alpha, L_diag=np.diag(L).copy(),
+             cond=np.linalg.cond(K), ref_year=res[:, 0], ref_mean=res[:, 1], ref_std=res[:, 2])
+
+
 if __name__ == "__main__":
     mu_3x3(); c1_small(); c2_small(); c3_small(); c3_grad_small(); c4_small()
     if os.path.isdir(REF):
         boston_soft()
+        co2_maunaloa()
     print("golden fixtures written to", HERE)
