@@ -24,7 +24,8 @@ from . import matrix_utils as MatrixUtils  # noqa: F401
 from . import batched  # noqa: F401
 from .ep_classification import (EpParameterEstimator, GpClassifier, MarginalLikelihoodEvaluator, SiteParams,  # noqa: F401
                                 AvgBasedStopCriterion, FixedSweeps, ClassifierInput, AfterEstimationClassifierInput,
-                                HyperParameterOptimInput)
+                                HyperParameterOptimInput, GradientHyperParamsOptimizer, ApacheCommonsOptimizer,
+                                MeshHyperParamsLogLikelihoodEvaluator, HyperParamsMeshValues)
 from .gp_optimizer import GPOptimizer, GPOInput, BreezeLbfgsOptimizer, ucb_with_gradient  # noqa: F401
 from .gp_ukf import (UnscentedKalmanFilter, GPUnscentedKalmanFilter, UnscentedTransformParams, UnscentedFilteringInput,  # noqa: F401
                      SsmModel, FilteringOutput)

@@ -178,3 +178,119 @@ class MarginalLikelihoodEvaluator:
         kf = self.kernelFunc.changeHyperParams(hyperParams)
         K = MU.buildKernelMatrix(kf, trainInput, handle=self._handle)
         return self.logLikelihoodWithKernelMatrixPassed(K, targets)
+
+
+# ---- gp/classification/HyperParamsOptimization.scala: the callers of MarginalLikelihoodEvaluator.logLikelihood -----------
+class GradientHyperParamsOptimizer:
+    """HyperParamsOptimization.scala:31-55: maximise the EP log marginal likelihood with a GradientBasedOptimizer
+    (optimization/Optimization.scala, `BreezeLbfgsOptimizer` in the shipped wiring).  Host control flow only: every
+    objective/gradient evaluation is one fused gpk_ep_nll_grad call (K build + EP sweeps + gradient on the device)."""
+
+    def __init__(self, marginalLikelihoodEvaluator: MarginalLikelihoodEvaluator, gradOptimizer):
+        self.marginalLikelihoodEvaluator, self.gradOptimizer = marginalLikelihoodEvaluator, gradOptimizer
+        self.evaluations = 0
+
+    def optimizeHyperParams(self, optimizationInput: ClassifierInput):
+        if optimizationInput.trainData is None:
+            raise LookupError("None.get")                                   # optimizationInput.trainData.get (:40)
+        targets = optimizationInput.targets
+        init = optimizationInput.initHyperParams
+
+        def funcWithGradient(hyperParams):
+            ll, der = self.marginalLikelihoodEvaluator.logLikelihood(optimizationInput.trainData, targets, np.asarray(hyperParams))
+            assert len(hyperParams) == len(der)                             # :43
+            self.evaluations += 1
+            return ll, der
+
+        optimized = self.gradOptimizer.maximize(funcWithGradient, np.asarray(init.toDenseVector, dtype=np.float64))
+        return init.fromDenseVector(np.asarray(optimized, dtype=np.float64))
+
+
+class ApacheCommonsOptimizer:
+    """HyperParamsOptimization.scala:57-136: commons-math3 NonLinearConjugateGradientOptimizer(POLAK_RIBIERE), stopped after 5
+    iterations (IterationLimitConvergenceChecker), MaxIter(10), MaxEval(20), GoalType.MAXIMIZE, with the reference's
+    value/gradient cache per point (:66-110).  commons-math 3.2 is un-vendored third-party code whose line search no reference
+    test pins; SciPy's Polak-Ribiere CG with the same iteration cap stands in, the evaluation cap and the cache are reproduced."""
+
+    def __init__(self, marginalLikelihoodEvaluator: MarginalLikelihoodEvaluator, iterationLimit: int = 5, maxEval: int = 20):
+        self.marginalLikelihoodEvaluator = marginalLikelihoodEvaluator
+        self.iterationLimit, self.maxEval = iterationLimit, maxEval
+        self.evaluations = 0
+
+    def optimizeHyperParams(self, optimizationInput: ClassifierInput):
+        from scipy.optimize import minimize as sp_minimize
+        if optimizationInput.trainData is None:
+            raise LookupError("None.get")
+        init = optimizationInput.initHyperParams
+        cache = {}
+        best = {"x": np.asarray(init.toDenseVector, dtype=np.float64), "v": -np.inf}
+
+        class _TooManyEvaluations(Exception):                                # org.apache.commons.math3.exception.TooManyEvaluationsException
+            pass
+
+        def value_and_gradient(p):
+            key = tuple(np.asarray(p, dtype=np.float64))
+            if key not in cache:                                             # pointGradientMapping (:66-110)
+                if self.evaluations >= self.maxEval:
+                    raise _TooManyEvaluations()
+                ll, g = self.marginalLikelihoodEvaluator.logLikelihood(optimizationInput.trainData, optimizationInput.targets,
+                                                                       np.asarray(p, dtype=np.float64))
+                self.evaluations += 1
+                cache[key] = (ll, np.asarray(g, dtype=np.float64))
+                if ll > best["v"]:
+                    best["x"], best["v"] = np.asarray(p, dtype=np.float64).copy(), ll
+            return cache[key]
+
+        try:
+            res = sp_minimize(lambda p: -value_and_gradient(p)[0], best["x"].copy(), jac=lambda p: -value_and_gradient(p)[1],
+                              method="CG", options={"maxiter": self.iterationLimit})
+            point = res.x if -res.fun >= best["v"] else best["x"]
+        except _TooManyEvaluations:
+            point = best["x"]
+        return init.fromDenseVector(np.asarray(point, dtype=np.float64))
+
+
+class HyperParamsMeshValues:
+    """MeshHyperParamsLogLikelihoodEvaluator.scala:51-90 (the Scala map is keyed by array identity; a list of pairs keeps
+    every entry the same way)."""
+
+    def __init__(self):
+        self.paramsLikelihood = []
+
+    def addResult(self, params, logLikelihood: float):
+        self.paramsLikelihood.append((np.array(params, dtype=np.float64), float(logLikelihood)))
+
+    def getLikelihood(self, params):
+        for p, v in self.paramsLikelihood:
+            if p is params:
+                return v
+        return None
+
+    def writeToFile(self, fileName: str):
+        with open(fileName, "w") as f:
+            for p, v in self.paramsLikelihood:
+                f.write("".join(f"{x}\t" for x in p) + f"{v}\n")
+
+
+class MeshHyperParamsLogLikelihoodEvaluator:
+    """MeshHyperParamsLogLikelihoodEvaluator.scala:12-45: EP log marginal likelihood on a mesh of hyper-parameter values.  As
+    written (:32-38) the likelihood is evaluated at `currentHyperParams` -- the point BEFORE the entry of this recursion level
+    is replaced -- and stored under the replaced copy; reproduced."""
+
+    def __init__(self, likelihoodEvaluator: MarginalLikelihoodEvaluator):
+        self.likelihoodEvaluator = likelihoodEvaluator
+
+    def evaluate(self, hyperParamsRanges, classificationContext: ClassifierInput) -> HyperParamsMeshValues:
+        init = np.array([r[0] for r in hyperParamsRanges], dtype=np.float64)     # hyperParamsRanges.map(_.start)
+        result = HyperParamsMeshValues()
+        self._rec(init, hyperParamsRanges, 0, classificationContext, result)
+        return result
+
+    def _rec(self, current, allRanges, rangeIndex, ctx, result):
+        for hyperParam in allRanges[rangeIndex]:
+            copied = current.copy()
+            copied[rangeIndex] = hyperParam
+            if rangeIndex + 1 < len(allRanges):
+                self._rec(copied, allRanges, rangeIndex + 1, ctx, result)
+            likelihood = self.likelihoodEvaluator.logLikelihoodWithoutGrad(ctx.trainData, ctx.targets, current)
+            result.addResult(copied, likelihood)

@@ -8,7 +8,11 @@
 //
 // Reference paths are relative to /root/reference/src/main/scala/.
 #pragma once
+#include <algorithm>
 #include <cmath>
+#include <deque>
+#include <functional>
+#include <limits>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -65,8 +69,20 @@ public:
         }
     }
     static Handle& instance() { static Handle h(0); return h; }   // the Scala objects are process-wide singletons too
+    void setGraphMode(bool on) const { check(gpk_set_graph_mode(h_, on ? 1 : 0)); }
 private:
     gpk_handle h_ = nullptr;
+};
+
+// how the (D, theta) arguments of the enclosed gpk_* calls are read (gpk_kernel_family); restored on scope exit
+class FamilyScope {
+public:
+    FamilyScope(Handle& h, int family) : h_(h), prev_(gpk_get_kernel_family(h.get())) { h_.check(gpk_set_kernel_family(h_.get(), family)); }
+    ~FamilyScope() { gpk_set_kernel_family(h_.get(), prev_); }
+    FamilyScope(const FamilyScope&) = delete;
+    FamilyScope& operator=(const FamilyScope&) = delete;
+private:
+    Handle& h_; int prev_;
 };
 
 // ---- utils/KernelRequisites.scala ------------------------------------------------------------------------------------
@@ -96,8 +112,17 @@ struct GaussianRbfParams {   // KernelRequisites.scala:39-60; signalVar / noiseV
 
 class GaussianRbfKernel {   // KernelRequisites.scala:62-114
 public:
+    using Params = GaussianRbfParams;
+    static constexpr int family = GPK_KERNEL_SE_ARD;
     explicit GaussianRbfKernel(GaussianRbfParams p) : rbfParams(std::move(p)) {}
     GaussianRbfParams rbfParams;
+    // theta as libgpk reads it for D-dimensional inputs, with the reference's own requirement (:55)
+    static DenseVector thetaFor(const GaussianRbfParams& hp, int D) {
+        DenseVector th = hp.toDenseVector();
+        if ((int)th.size() != D + 2)
+            throw IllegalArgumentException("requirement failed: " + std::to_string(th.size()) + " does not equal to " + std::to_string(D + 2));
+        return th;
+    }
     int hyperParametersNum() const { return (int)rbfParams.lengthScales.size() + 2; }
     const GaussianRbfParams& hyperParams() const { return rbfParams; }
     GaussianRbfKernel changeHyperParams(const DenseVector& dv) const { return GaussianRbfKernel(rbfParams.fromDenseVector(dv)); }
@@ -113,19 +138,130 @@ public:
     }
 };
 
+
+// ---- gp/regression/Co2Prediction.scala:16-137: the second closed-form KernelFunc (1-D inputs, 11 hyper-parameters) ----------
+struct Co2HyperParams {   // :18-27, a bare DenseVector; getAtPosition is 1-based (dv(i - 1))
+    DenseVector dv;
+    double getAtPosition(int i) const {
+        if (i < 1 || i > (int)dv.size()) throw std::out_of_range("java.lang.IndexOutOfBoundsException: " + std::to_string(i - 1));
+        return dv[i - 1];
+    }
+    DenseVector toDenseVector() const { return dv; }
+    Co2HyperParams fromDenseVector(const DenseVector& v) const { return Co2HyperParams{v}; }   // no length requirement (:20)
+};
+
+class Co2Kernel {
+public:
+    using Params = Co2HyperParams;
+    static constexpr int family = GPK_KERNEL_CO2;
+    explicit Co2Kernel(Co2HyperParams p) : co2HyperParams(std::move(p)) {}
+    Co2HyperParams co2HyperParams;
+    int hyperParametersNum() const { return 11; }   // :85
+    const Co2HyperParams& hyperParams() const { return co2HyperParams; }
+    Co2Kernel changeHyperParams(const DenseVector& dv) const { return Co2Kernel(Co2HyperParams{dv}); }
+    DenseVector theta() const { return thetaFor(co2HyperParams, 1); }
+    static DenseVector thetaFor(const Co2HyperParams& hp, int D) {
+        if (D != 1) throw IllegalArgumentException("requirement failed: This kernel is applicable only for 1D objects");   // :39
+        DenseVector th(11);
+        for (int i = 1; i <= 11; ++i) th[i - 1] = hp.getAtPosition(i);   // getHyperParams :87-92
+        return th;
+    }
+    double apply(const DenseVector& a, const DenseVector& b, bool sameIndex) const {   // :38-56
+        if (a.size() != 1 || b.size() != 1) throw IllegalArgumentException("requirement failed: This kernel is applicable only for 1D objects");
+        const DenseVector h = theta();
+        const double xDiff = a[0] - b[0], xDiffSq = xDiff * xDiff;
+        const double k1 = h[0] * h[0] * std::exp(-xDiffSq / (2 * h[1] * h[1]));
+        const double sinVal = std::sin(3.14159265358979323846 * xDiff);
+        const double k2 = h[2] * h[2] * std::exp((-xDiffSq / (2 * h[3] * h[3])) - 2 * sinVal * sinVal / (h[4] * h[4]));
+        const double k3 = h[5] * h[5] * std::pow(1 + xDiffSq / (2 * h[7] * h[6] * h[6]), -h[7]);
+        const double k4 = h[8] * h[8] * std::exp(-xDiffSq / (2 * h[9] * h[9]));
+        return k1 + k2 + k3 + k4 + (sameIndex ? h[10] * h[10] : 0.);
+    }
+};
+
+// ---- optimization/Optimization.scala:30-61 -----------------------------------------------------------------------------------
+// BreezeLbfgsOptimizer: L-BFGS(m = 4, maxIter) with the reference's best-seen bookkeeping (:37-55).  Breeze's LBFGS is un-vendored
+// third-party code whose trajectory no reference test pins; a textbook two-loop L-BFGS with an Armijo backtracking line search
+// stands in (host control flow: each evaluation of `func` is one device call).
+using objectiveFunctionWithGradient = std::function<std::pair<double, DenseVector>(const DenseVector&)>;
+class BreezeLbfgsOptimizer {
+public:
+    explicit BreezeLbfgsOptimizer(int maxIter = 10, int m = 4) : maxIter_(maxIter), m_(m) {}
+    int evaluations = 0;
+    DenseVector minimize(const objectiveFunctionWithGradient& func, const DenseVector& initPoint) {
+        DenseVector bestX = initPoint; double bestV = std::numeric_limits<double>::max();     // :38-39
+        auto calc = [&](const DenseVector& x) {
+            auto r = func(x); ++evaluations;
+            if (r.first < bestV) { bestV = r.first; bestX = x; }                               // :44-46
+            return r;
+        };
+        const size_t n = initPoint.size();
+        DenseVector x = initPoint;
+        auto [f, g] = calc(x);
+        std::deque<std::pair<DenseVector, DenseVector>> hist;   // (s, y)
+        auto dot = [n](const DenseVector& a, const DenseVector& b) { double s = 0; for (size_t i = 0; i < n; ++i) s += a[i] * b[i]; return s; };
+        for (int it = 0; it < maxIter_; ++it) {
+            if (std::sqrt(dot(g, g)) <= 1e-9 * std::max(1.0, std::fabs(f))) break;
+            DenseVector d = g; std::vector<double> a(hist.size());
+            for (int k = (int)hist.size() - 1; k >= 0; --k) {
+                a[k] = dot(hist[k].first, d) / dot(hist[k].first, hist[k].second);
+                for (size_t i = 0; i < n; ++i) d[i] -= a[k] * hist[k].second[i];
+            }
+            if (!hist.empty()) {
+                const double gam = dot(hist.back().first, hist.back().second) / dot(hist.back().second, hist.back().second);
+                for (auto& v : d) v *= gam;
+            }
+            for (size_t k = 0; k < hist.size(); ++k) {
+                const double b = dot(hist[k].second, d) / dot(hist[k].first, hist[k].second);
+                for (size_t i = 0; i < n; ++i) d[i] += (a[k] - b) * hist[k].first[i];
+            }
+            for (auto& v : d) v = -v;
+            double slope = dot(g, d);
+            if (!(slope < 0)) { d = g; for (auto& v : d) v = -v; slope = -dot(g, g); hist.clear(); }
+            double step = hist.empty() ? 1.0 / std::max(1.0, std::sqrt(dot(g, g))) : 1.0;
+            DenseVector xn(n), gn; double fn = f; bool ok = false;
+            for (int ls = 0; ls < 20; ++ls, step *= 0.5) {
+                for (size_t i = 0; i < n; ++i) xn[i] = x[i] + step * d[i];
+                auto r = calc(xn); fn = r.first; gn = std::move(r.second);
+                if (std::isfinite(fn) && fn <= f + 1e-4 * step * slope) { ok = true; break; }
+            }
+            if (!ok) break;
+            DenseVector sv(n), yv(n);
+            for (size_t i = 0; i < n; ++i) { sv[i] = xn[i] - x[i]; yv[i] = gn[i] - g[i]; }
+            if (dot(sv, yv) > 1e-12 * std::sqrt(dot(sv, sv) * dot(yv, yv))) {
+                hist.emplace_back(std::move(sv), std::move(yv));
+                if ((int)hist.size() > m_) hist.pop_front();
+            }
+            x = xn; f = fn; g = gn;
+        }
+        const double optimalVal = func(x).first;                  // :52
+        return optimalVal < bestV ? x : bestX;                    // :53-55
+    }
+    DenseVector maximize(const objectiveFunctionWithGradient& func, const DenseVector& initPoint) {   // :58-60
+        return minimize([&](const DenseVector& p) { auto r = func(p); for (auto& v : r.second) v = -v; return std::make_pair(-r.first, std::move(r.second)); },
+                        initPoint);
+    }
+private:
+    int maxIter_, m_;
+};
+
 // ---- utils/MatrixUtils.scala (+ breeze cholesky) -----------------------------------------------------------------------
 namespace MatrixUtils {
-inline DenseMatrix buildKernelMatrix(const GaussianRbfKernel& k, const DenseMatrix& data, Handle& h = Handle::instance()) {   // :57-70
+template <class Kernel>
+inline DenseMatrix buildKernelMatrix(const Kernel& k, const DenseMatrix& data, Handle& h = Handle::instance()) {   // :57-70
     DenseMatrix K(data.rows, data.rows);
-    const DenseVector th = k.theta();
+    const DenseVector th = Kernel::thetaFor(k.hyperParams(), data.cols);
+    FamilyScope fam(h, Kernel::family);
     h.check(gpk_cov_se_ard(h.get(), data.data.data(), data.rows, data.cols, data.rows, th.data(), K.data.data(), data.rows));
     return K;
 }
-inline DenseMatrix buildKernelMatrix(const GaussianRbfKernel& k, const DenseMatrix& in1, const DenseMatrix& in2,
+template <class Kernel>
+inline DenseMatrix buildKernelMatrix(const Kernel& k, const DenseMatrix& in1, const DenseMatrix& in2,
                                      Handle& h = Handle::instance()) {                                                      // :44-55
     if (in1.cols != in2.cols) throw IllegalArgumentException("requirement failed: feature dimensions differ");
     DenseMatrix K(in1.rows, in2.rows);
-    const DenseVector th = k.theta();
+    const DenseVector th = Kernel::thetaFor(k.hyperParams(), in1.cols);
+    FamilyScope fam(h, Kernel::family);
     h.check(gpk_cov_cross_se_ard(h.get(), in1.data.data(), in1.rows, in1.rows, in2.data.data(), in2.rows, in2.rows, in1.cols, th.data(),
                                  K.data.data(), in1.rows));
     return K;
@@ -172,17 +308,63 @@ struct PredictionInput {                                                        
     PredictionTrainingInput toPredictionTrainingInput() const { return {trainingData, sigmaNoise, targets}; }
 };
 
-class GpPredictor {
+// Device-resident (X, L^-1, alpha, theta): the fit-once / predict-many pattern of GP-UKF and GP-UCB
+// (GPUnscentedKalmanFilter.scala:77-88,123-147; GPOptimizer.scala:48-109) without moving L across PCIe.
+class FittedGp {
 public:
-    explicit GpPredictor(GaussianRbfKernel k, Handle& h = Handle::instance()) : kernelFunc(std::move(k)), h_(h) {}
-    GaussianRbfKernel kernelFunc;
+    FittedGp(Handle& h, gpk_model m, int n, int D, double ll, std::optional<double> sigmaNoise)
+        : logLikelihood(ll), h_(h), m_(m), n_(n), D_(D), sigmaNoise_(sigmaNoise) {}
+    FittedGp(FittedGp&& o) noexcept : logLikelihood(o.logLikelihood), h_(o.h_), m_(o.m_), n_(o.n_), D_(o.D_), sigmaNoise_(o.sigmaNoise_) { o.m_ = nullptr; }
+    FittedGp(const FittedGp&) = delete;
+    FittedGp& operator=(const FittedGp&) = delete;
+    ~FittedGp() { if (m_) gpk_gp_model_destroy(h_.get(), m_); }
+    double logLikelihood;
+    int size() const { return n_; }
+    // GpPredictor.scala:45-58 computePosterior -> (GaussianDistribution, vMatrix)
+    std::pair<GaussianDistribution, DenseMatrix> computePosterior(const DenseMatrix& Xs) const;
+    DenseVector mean(const DenseMatrix& Xs) const {   // K* alpha only (GPUnscentedKalmanFilter.scala:77-90 reads nothing else)
+        DenseVector mu(Xs.rows);
+        h_.check(gpk_gp_model_predict(h_.get(), m_, Xs.data.data(), Xs.rows, Xs.rows, 0, mu.data(), nullptr, Xs.rows, nullptr, n_));
+        return mu;
+    }
+    DenseVector alphaVec() const { DenseVector a(n_); h_.check(gpk_gp_model_get_alpha(h_.get(), m_, a.data())); return a; }
+    // GPOptimizer.scala:64-71 + :51: one more evaluated point, hyper-parameters unchanged -> bordered O(n^2) update
+    void append(const DenseVector& point, double target) {
+        if ((int)point.size() != D_) throw IllegalArgumentException("requirement failed: point dimension");
+        double d = 0.0;
+        h_.check(gpk_gp_model_append(h_.get(), m_, point.data(), target, sigmaNoise_.has_value(), sigmaNoise_.value_or(0.0), &d));
+        ++n_; logLikelihood += d;
+    }
+    // GPOptimizer.scala:87-104: maximizeUCB's objective and gradient at the rows of Xs -> (ucb[m], grad m x D)
+    std::pair<DenseVector, DenseMatrix> ucbWithGradient(const DenseMatrix& Xs, double kParam) const {
+        DenseVector ucb(Xs.rows); DenseMatrix grad(Xs.rows, D_);
+        h_.check(gpk_gp_model_ucb(h_.get(), m_, Xs.data.data(), Xs.rows, Xs.rows, kParam, ucb.data(), grad.data.data(), Xs.rows, nullptr, nullptr));
+        return {std::move(ucb), std::move(grad)};
+    }
+private:
+    Handle& h_; gpk_model m_; int n_, D_; std::optional<double> sigmaNoise_;
+};
+inline std::pair<GaussianDistribution, DenseMatrix> FittedGp::computePosterior(const DenseMatrix& Xs) const {
+    GaussianDistribution d{DenseVector(Xs.rows), DenseMatrix(Xs.rows, Xs.rows)}; DenseMatrix V(n_, Xs.rows);
+    h_.check(gpk_gp_model_predict(h_.get(), m_, Xs.data.data(), Xs.rows, Xs.rows, 1, d.mean.data(), d.sigma.data.data(), Xs.rows,
+                                  V.data.data(), n_));
+    return {std::move(d), std::move(V)};
+}
+
+template <class Kernel>
+class GpPredictorT {
+public:
+    using Params = typename Kernel::Params;
+    explicit GpPredictorT(Kernel k, Handle& h = Handle::instance()) : kernelFunc(std::move(k)), h_(h) {}
+    Kernel kernelFunc;
 
     // :104-124 -> (L, alphaVec, Option[sigmaNoise * I])
     std::tuple<DenseMatrix, DenseVector, std::optional<DenseMatrix>> preComputeComponents(
-        const DenseMatrix& X, const GaussianRbfParams& hp, std::optional<double> sigmaNoise, const DenseVector& targets) const {
+        const DenseMatrix& X, const Params& hp, std::optional<double> sigmaNoise, const DenseVector& targets) const {
         require_rows(X, targets);
-        const DenseVector th = theta_for(hp, X.cols);
+        const DenseVector th = Kernel::thetaFor(hp, X.cols);
         DenseMatrix L(X.rows, X.rows); DenseVector alpha(X.rows); double ll = 0.0;
+        FamilyScope fam(h_, Kernel::family);
         h_.check(gpk_gp_fit(h_.get(), X.data.data(), X.rows, X.cols, X.rows, targets.data(), th.data(), sigmaNoise.has_value(),
                             sigmaNoise.value_or(0.0), L.data.data(), X.rows, alpha.data(), &ll));
         std::optional<DenseMatrix> noise;
@@ -190,23 +372,25 @@ public:
         return {std::move(L), std::move(alpha), std::move(noise)};
     }
     // :60-80 -> (logLikelihood, gradient[optimizedParamsNum])
-    std::pair<double, DenseVector> logLikelihoodWithDerivatives(const PredictionTrainingInput& in, const GaussianRbfParams& hp,
+    std::pair<double, DenseVector> logLikelihoodWithDerivatives(const PredictionTrainingInput& in, const Params& hp,
                                                                 int optimizedParamsNum) const {
         require_rows(in.trainingData, in.targets);
         const DenseMatrix& X = in.trainingData;
-        const DenseVector th = theta_for(hp, X.cols);
+        const DenseVector th = Kernel::thetaFor(hp, X.cols);
         double ll = 0.0; DenseVector g(std::max(optimizedParamsNum, 1), 0.0);
+        FamilyScope fam(h_, Kernel::family);
         h_.check(gpk_gp_nll_grad(h_.get(), X.data.data(), X.rows, X.cols, X.rows, in.targets.data(), th.data(), in.sigmaNoise.has_value(),
                                  in.sigmaNoise.value_or(0.0), optimizedParamsNum, &ll, g.data()));
         g.resize(optimizedParamsNum);
         return {ll, std::move(g)};
     }
     // :24-43 -> (GaussianDistribution(mean, sigma), logLikelihood); the sigma diagonal includes noiseVar^2 (+ sigmaNoise)
-    std::pair<GaussianDistribution, double> predict(const PredictionInput& in, const GaussianRbfParams& hp) const {
+    std::pair<GaussianDistribution, double> predict(const PredictionInput& in, const Params& hp) const {
         require_rows(in.trainingData, in.targets);
         const DenseMatrix &X = in.trainingData, &Xs = in.testData;
-        const DenseVector th = theta_for(hp, X.cols);
+        const DenseVector th = Kernel::thetaFor(hp, X.cols);
         GaussianDistribution d{DenseVector(Xs.rows), DenseMatrix(Xs.rows, Xs.rows)}; double ll = 0.0;
+        FamilyScope fam(h_, Kernel::family);
         h_.check(gpk_gp_predict(h_.get(), X.data.data(), X.rows, X.cols, X.rows, in.targets.data(), Xs.data.data(), Xs.rows, Xs.rows,
                                 th.data(), in.sigmaNoise.has_value(), in.sigmaNoise.value_or(0.0), d.mean.data(), d.sigma.data.data(),
                                 Xs.rows, &ll));
@@ -216,16 +400,46 @@ public:
     // :45-58 computePosterior(trainingData, testData, l, alphaVec, kernelFunc) -> (GaussianDistribution, vMatrix)
     std::pair<GaussianDistribution, DenseMatrix> computePosterior(const DenseMatrix& X, const DenseMatrix& Xs, const DenseMatrix& l,
                                                                   const DenseVector& alphaVec) const {
-        const DenseVector th = kernelFunc.theta();
+        const DenseVector th = Kernel::thetaFor(kernelFunc.hyperParams(), X.cols);
         gpk_model m = nullptr;
-        h_.check(gpk_gp_model_from_factor(h_.get(), X.data.data(), X.rows, X.cols, X.rows, l.data.data(), l.rows, alphaVec.data(),
-                                          th.data(), &m));
-        GaussianDistribution d{DenseVector(Xs.rows), DenseMatrix(Xs.rows, Xs.rows)}; DenseMatrix V(X.rows, Xs.rows);
-        const int rc = gpk_gp_model_predict(h_.get(), m, Xs.data.data(), Xs.rows, Xs.rows, 1, d.mean.data(), d.sigma.data.data(), Xs.rows,
-                                            V.data.data(), X.rows);
-        gpk_gp_model_destroy(h_.get(), m);
-        h_.check(rc);
-        return {std::move(d), std::move(V)};
+        {
+            FamilyScope fam(h_, Kernel::family);
+            h_.check(gpk_gp_model_from_factor(h_.get(), X.data.data(), X.rows, X.cols, X.rows, l.data.data(), l.rows, alphaVec.data(),
+                                              th.data(), &m));
+        }
+        return FittedGp(h_, m, X.rows, X.cols, 0.0, std::nullopt).computePosterior(Xs);
+    }
+    // resident preComputeComponents
+    FittedGp fit(const DenseMatrix& X, std::optional<double> sigmaNoise, const DenseVector& targets, const Params& hp) const {
+        require_rows(X, targets);
+        const DenseVector th = Kernel::thetaFor(hp, X.cols);
+        gpk_model m = nullptr; double ll = 0.0;
+        FamilyScope fam(h_, Kernel::family);
+        h_.check(gpk_gp_model_fit(h_.get(), X.data.data(), X.rows, X.cols, X.rows, targets.data(), th.data(), sigmaNoise.has_value(),
+                                  sigmaNoise.value_or(0.0), &m, &ll));
+        return FittedGp(h_, m, X.rows, X.cols, ll, sigmaNoise);
+    }
+    // :126-142: L-BFGS(m = 4, maxIter = 20) maximisation of logLikelihoodWithDerivatives in the natural parameters.  optimizeNoise =
+    // false reproduces the reference's defect: the start point drops the last entry (`toDenseVector(0 to -2)`) and the first
+    // evaluation fails in fromDenseVector's require (KernelRequisites.scala:55) / getAtPosition(11) (Co2Prediction.scala:23).
+    Params obtainOptimalHyperParams(const DenseMatrix& X, std::optional<double> sigmaNoise, const DenseVector& targets, bool optimizeNoise,
+                                    int maxIter = 20) const {
+        BreezeLbfgsOptimizer opt(maxIter);
+        const Params hp0 = kernelFunc.hyperParams();
+        DenseVector init = hp0.toDenseVector();
+        if (!optimizeNoise) init.pop_back();
+        const PredictionTrainingInput ptInput{X, sigmaNoise, targets};
+        auto llObjFunction = [&](const DenseVector& currentParams) {
+            const Params hp = hp0.fromDenseVector(currentParams);
+            return logLikelihoodWithDerivatives(ptInput, hp, (int)currentParams.size());
+        };
+        return hp0.fromDenseVector(opt.maximize(llObjFunction, init));
+    }
+    // :82-87 -> (posterior, logLikelihood, optimal hyper-parameters)
+    std::tuple<GaussianDistribution, double, Params> predictWithParamsOptimization(const PredictionInput& in, bool optimizeNoise) const {
+        Params optimal = obtainOptimalHyperParams(in.trainingData, in.sigmaNoise, in.targets, optimizeNoise);
+        auto r = predict(in, optimal);
+        return {std::move(r.first), r.second, std::move(optimal)};
     }
 
 private:
@@ -234,13 +448,9 @@ private:
         if (X.rows != (int)y.size())
             throw IllegalArgumentException("requirement failed: Number of objects in training data matrix should be equal to targets vector length");
     }
-    static DenseVector theta_for(const GaussianRbfParams& hp, int D) {
-        DenseVector th = hp.toDenseVector();
-        if ((int)th.size() != D + 2)
-            throw IllegalArgumentException("requirement failed: " + std::to_string(th.size()) + " does not equal to " + std::to_string(D + 2));
-        return th;
-    }
 };
+using GpPredictor = GpPredictorT<GaussianRbfKernel>;   // spring-context.xml:33-47
+using Co2GpPredictor = GpPredictorT<Co2Kernel>;        // spring-context.xml:49-51 "co2GpPredictor"
 
 // ---- gp/classification/{EpParameterEstimator, GpClassifier}.scala ------------------------------------------------------
 struct SiteParams { DenseVector tauSiteParams, niSiteParams; std::optional<double> marginalLogLikelihood; };   // EpParameterEstimator.scala:181-182

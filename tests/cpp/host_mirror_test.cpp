@@ -75,6 +75,46 @@ int main(int argc, char** argv) {
         try { DenseMatrix B = DenseMatrix::eye(5); B(3, 3) = -1.0; MatrixUtils::cholesky(B); } catch (const NotConvergedException& e) { if (e.minor == 4) errors |= 2; }
         try { hp.getAtPosition(D + 3); } catch (const MatchError&) { errors |= 4; }
         try { DenseMatrix B(2, 2); B(0, 0) = B(1, 1) = 1.0; B(0, 1) = 2.0; B(1, 0) = 3.0; MatrixUtils::cholesky(B); } catch (const MatrixNotSymmetricException&) { errors |= 8; }
+        // GpPredictor.obtainOptimalHyperParams (GpPredictor.scala:126-142) through the C++ L-BFGS wrapper: every evaluation is a device call
+        GaussianRbfParams opt = pred.obtainOptimalHyperParams(X, std::nullopt, y, true);
+        put(out, "opt_theta", opt.toDenseVector());
+        put(out, "opt_ll", DenseVector{pred.logLikelihoodWithDerivatives(PredictionTrainingInput{X, std::nullopt, y}, opt, 0).first});
+        try { pred.obtainOptimalHyperParams(X, std::nullopt, y, false); } catch (const IllegalArgumentException&) { errors |= 16; }
+        // resident model: fit on all but the last 3 rows, append them one by one (GPOptimizer.scala:48-71), posterior + UCB
+        {
+            DenseMatrix Xh(n - 3, D); DenseVector yh(y.begin(), y.end() - 3);
+            for (int c = 0; c < D; ++c) for (int r = 0; r < n - 3; ++r) Xh(r, c) = X(r, c);
+            FittedGp model = pred.fit(Xh, std::nullopt, yh, hp);
+            for (int r = n - 3; r < n; ++r) { DenseVector pt(D); for (int c = 0; c < D; ++c) pt[c] = X(r, c); model.append(pt, y[r]); }
+            put(out, "model_size", DenseVector{(double)model.size()});
+            put(out, "model_ll", DenseVector{model.logLikelihood});
+            put(out, "model_alpha", model.alphaVec());
+            put(out, "model_mean", model.mean(Xs));
+            auto [ucb, ugrad] = model.ucbWithGradient(Xs, 1.5);
+            put(out, "model_ucb", ucb);
+            put(out, "model_ucb_grad", ugrad.data);
+        }
+        // Co2Kernel (Co2Prediction.scala:29-137) through the same predictor template: 1-D inputs on a year axis
+        {
+            DenseMatrix T(n, 1), Ts(m, 1); DenseVector yc(n);
+            for (int r = 0; r < n; ++r) { T(r, 0) = 1958.0 + 30.0 * X(r, 0); yc[r] = 330.0 + 10.0 * y[r]; }
+            for (int r = 0; r < m; ++r) Ts(r, 0) = 1958.0 + 30.0 * Xs(r, 0);
+            Co2HyperParams chp{DenseVector{60., 70., 8., 50., 2., 0.34, 2.4, 0.88, 0.26, 0.2, 1.5}};
+            Co2Kernel ck(chp);
+            Co2GpPredictor cpred(ck);
+            auto [cll, cgrad] = cpred.logLikelihoodWithDerivatives(PredictionTrainingInput{T, std::nullopt, yc}, chp, 11);
+            put(out, "co2_ll", DenseVector{cll});
+            put(out, "co2_grad", cgrad);
+            auto [cdist, cll2] = cpred.predict(PredictionInput{T, Ts, std::nullopt, yc}, chp);
+            put(out, "co2_mean", cdist.mean);
+            DenseMatrix Kc = MatrixUtils::buildKernelMatrix(ck, T);
+            put(out, "co2_K_row0", [&] { DenseVector d(n); for (int i = 0; i < n; ++i) d[i] = Kc(0, i); return d; }());
+            put(out, "co2_apply", DenseVector{ck.apply({T(0, 0)}, {T(1, 0)}, false), ck.apply({T(0, 0)}, {T(0, 0)}, true)});
+            try { cpred.logLikelihoodWithDerivatives(PredictionTrainingInput{X, std::nullopt, y}, chp, 11); } catch (const IllegalArgumentException&) { errors |= 32; }
+            try { cpred.obtainOptimalHyperParams(T, std::nullopt, yc, false); } catch (const std::out_of_range&) { errors |= 64; }
+        }
+        // the SE family is back in force afterwards
+        put(out, "ll_again", DenseVector{pred.logLikelihoodWithDerivatives(PredictionTrainingInput{X, std::nullopt, y}, hp, 0).first});
         put(out, "errors_caught", DenseVector{(double)errors}, true);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "host_mirror_test failed: %s\n", e.what());

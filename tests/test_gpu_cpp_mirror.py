@@ -51,4 +51,32 @@ def test_cpp_mirror_matches_oracle(tmp_path):
     Ks = orc.fast_build_kernel_matrix(Xs, th, X); Kss = orc.fast_build_kernel_matrix(Xs, th)
     po, _, _ = orc.fast_ep_classify(K, Ks, Kss, e["tau"], e["nu"], e["L"])
     assert rel(o["ep_prob"], po)
-    assert int(o["errors_caught"][0]) == 15      # IllegalArgument, NotConverged(minor 4), MatchError, MatrixNotSymmetric
+    # IllegalArgument, NotConverged(minor 4), MatchError, MatrixNotSymmetric, optimizeNoise=false defect (SE: require, Co2: index), Co2 on 3-D data
+    assert int(o["errors_caught"][0]) == 127
+    # obtainOptimalHyperParams: the reported optimum is a point of the oracle's objective and not worse than the start
+    th_opt = np.array(o["opt_theta"])
+    assert abs(o["opt_ll"][0] - orc.fast_loglik_with_derivs(X, y, th_opt, None, 0)[0]) <= 1e-9 * abs(o["opt_ll"][0])
+    assert o["opt_ll"][0] >= llo
+    assert o["ll_again"][0] == o["ll"][0]
+    # resident model after three appends == refit on all rows
+    assert int(o["model_size"][0]) == n
+    assert rel(o["model_alpha"], alpha) and abs(o["model_ll"][0] - llo) <= 1e-9 * abs(llo)
+    assert rel(o["model_mean"], mp)
+    Ll, al = orc.lit_precompute(X, y, th)
+    ug = np.array(o["model_ucb_grad"]).reshape(D, m).T
+    for i in (0, m - 1):
+        u_o, g_o, _, _ = orc.lit_ucb_with_grad(X, Ll, al, th, Xs[i], 1.5)
+        assert abs(o["model_ucb"][i] - u_o) <= 1e-9 * max(abs(u_o), 1e-3) and rel(ug[i], g_o)
+    # Co2Kernel through the same template
+    T, Ts, yc = 1958.0 + 30.0 * X[:, :1], 1958.0 + 30.0 * Xs[:, :1], 330.0 + 10.0 * y
+    chp = np.array([60., 70., 8., 50., 2., 0.34, 2.4, 0.88, 0.26, 0.2, 1.5])
+    with orc.co2_kernel():
+        Kc = orc.lit_build_kernel_matrix(T, chp)
+        tol = 1e-9 * max(1.0, np.linalg.cond(Kc) / 1e5)
+        cll, cg = orc.lit_loglik_with_derivs(T, yc, chp, None)
+        cm, _, _ = orc.lit_predict(T, yc, Ts, chp, None)
+    assert abs(o["co2_ll"][0] - cll) <= tol * abs(cll) and rel(o["co2_grad"], cg, tol)
+    assert np.all(np.abs(np.array(o["co2_mean"]) - cm) <= tol * np.abs(cm).max())
+    assert np.abs(np.array(o["co2_K_row0"]) - Kc[0]).max() <= 8 * np.finfo(float).eps * np.abs(Kc).max()
+    assert abs(o["co2_apply"][0] - orc.co2_k(T[0, 0], T[1, 0], chp, False)) <= 4e-16 * abs(o["co2_apply"][0])
+    assert abs(o["co2_apply"][1] - orc.co2_k(T[0, 0], T[0, 0], chp, True)) <= 4e-16 * abs(o["co2_apply"][1])

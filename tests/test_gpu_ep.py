@@ -146,3 +146,51 @@ def test_c3_config_full_size_properties():
     assert np.array_equal(site2.tauSiteParams, tau) and site2.marginalLogLikelihood == site.marginalLogLikelihood
     p = gp.GpClassifier(gp.FixedSweeps(3)).classify(gp.AfterEstimationClassifierInput(t, (site, L), None, K, K[:64], K[:64, :64]))
     assert np.all((p > 0) & (p < 1)) and np.mean((p > 0.5) == (t[:64] > 0)) > 0.85
+
+
+# ---- callers of MarginalLikelihoodEvaluator (HyperParamsOptimization.scala, MeshHyperParamsLogLikelihoodEvaluator.scala) ----
+def test_classification_hyperparameter_optimisers():
+    X, t, th = orc.make_c3(n=180, D=2, seed=31)
+    th = np.array([0.8, 2.0, 2.0, 0.2])
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
+    ev = gp.MarginalLikelihoodEvaluator(gp.FixedSweeps(3), kf)
+    ll0, g0 = ev.logLikelihood(X, t, th)
+    ctx = gp.ClassifierInput(None, t, kf.hyperParams, X)
+    opt = gp.GradientHyperParamsOptimizer(ev, gp.BreezeLbfgsOptimizer(maxIter=6))
+    hp = opt.optimizeHyperParams(ctx)
+    assert isinstance(hp, gp.GaussianRbfParams) and opt.evaluations >= 2
+    # every evaluation the optimiser saw is the oracle's objective: check the returned point
+    ll1, g1 = ev.logLikelihood(X, t, hp.toDenseVector)
+    lz_o, g_o, _ = orc.lit_ep_loglik_with_derivs(X, t, hp.toDenseVector, fixed_sweeps=3)
+    assert abs(ll1 - lz_o) <= RTOL * abs(lz_o) and close(g1, g_o)
+    assert ll1 >= ll0                                      # best-seen logic of Optimization.scala:44-55
+    cg = gp.ApacheCommonsOptimizer(ev)
+    hp2 = cg.optimizeHyperParams(ctx)
+    assert cg.evaluations <= 20                            # MaxEval(20), HyperParamsOptimization.scala:121
+    assert ev.logLikelihood(X, t, hp2.toDenseVector)[0] >= ll0
+    with pytest.raises(LookupError):                       # trainData.get on None (:40)
+        opt.optimizeHyperParams(gp.ClassifierInput(None, t, kf.hyperParams, None))
+
+
+def test_mesh_evaluator_reproduces_the_reference_loop():
+    X, t, th = orc.make_c3(n=90, D=1, seed=32)
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(1.0, [1.0], 0.1))
+    ev = gp.MarginalLikelihoodEvaluator(gp.FixedSweeps(2), kf)
+    ranges = [[0.5, 1.0], [0.7, 1.4, 2.1], [0.1]]
+    res = gp.MeshHyperParamsLogLikelihoodEvaluator(ev).evaluate(ranges, gp.ClassifierInput(None, t, kf.hyperParams, X))
+    # one entry per loop iteration at every level: 2 * (1 + 3 * (1 + 1))
+    assert len(res.paramsLikelihood) == 14
+    K = orc.lit_build_kernel_matrix
+    def lz(p):
+        site = orc.lit_ep_estimate(K(X, np.asarray(p)), t, fixed_sweeps=2)
+        return site["logZ"]
+    # innermost level: stored under (a, b, 0.1), evaluated at the point before its own entry was replaced = (a, b, start) = same
+    # middle level: stored under (a, b, start2), evaluated at (a, start1, start2) -- the quirk of :32-38
+    p_last, v_last = res.paramsLikelihood[-1]
+    assert np.array_equal(p_last, [1.0, 0.7, 0.1])          # outer level, second value
+    assert abs(v_last - lz([0.5, 0.7, 0.1])) <= RTOL * abs(v_last)     # ... evaluated at the start point
+    p_mid, v_mid = res.paramsLikelihood[3]                   # order: (0.5,0.7,[0.1]) inner, (0.5,0.7) mid, (0.5,1.4,[0.1]) inner, mid...
+    assert np.array_equal(res.paramsLikelihood[0][0], [0.5, 0.7, 0.1])
+    assert np.array_equal(res.paramsLikelihood[1][0], [0.5, 0.7, 0.1])
+    assert np.array_equal(p_mid, [0.5, 1.4, 0.1]) and abs(v_mid - lz([0.5, 0.7, 0.1])) <= RTOL * abs(v_mid)
+    assert abs(res.paramsLikelihood[2][1] - lz([0.5, 1.4, 0.1])) <= RTOL * abs(res.paramsLikelihood[2][1])
