@@ -138,9 +138,10 @@ class Handle:
     def launch_count(self) -> int:
         return int(self.lib.gpk_launch_count(self._h))
 
-    def set_graph_mode(self, on: bool):
-        """CUDA-graph replay of repeated logLikelihoodWithDerivatives calls (include/gpk.h); on by default."""
-        self.check(self.lib.gpk_set_graph_mode(self._h, 1 if on else 0))
+    def set_graph_mode(self, on):
+        """CUDA-graph replay of repeated launch sequences (include/gpk.h): False / 0 eager only, True / 1 default policy,
+        2 capture at the first repetition."""
+        self.check(self.lib.gpk_set_graph_mode(self._h, int(on)))
 
     def kernel_family(self, family: int):
         """`with h.kernel_family(GPK_KERNEL_CO2): ...` -- how the (D, theta) arguments of the enclosed calls are read

@@ -133,7 +133,7 @@ int gpk_destroy(gpk_handle h) {
     if (!h) return GPK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    gpk_eval_graph_drop(h);
+    gpk_graph_drop_all(h);
     for (int i = 0; i < GPK_NSIDE; ++i)
         if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
     for (int i = 0; i < GPK_NPIPE; ++i)
@@ -164,8 +164,8 @@ int gpk_get_kernel_family(gpk_handle h) { return h ? h->kernel_family : GPK_EINV
 int gpk_theta_length(gpk_handle h, int D) { return h ? gpk_theta_len(h, D) : GPK_EINVAL; }
 int gpk_set_graph_mode(gpk_handle h, int on) {
     if (!h) return GPK_EINVAL;
-    h->graph_mode = on ? 1 : 0;
-    if (!on) { cudaStreamSynchronize(h->stream); gpk_eval_graph_drop(h); }
+    h->graph_mode = on < 0 ? 0 : (on > 2 ? 2 : on);
+    if (!on) { cudaStreamSynchronize(h->stream); gpk_graph_drop_all(h); }
     return GPK_OK;
 }
 

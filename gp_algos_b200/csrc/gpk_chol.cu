@@ -249,7 +249,7 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     GPK_CUDA(h, cudaEventRecord(ev, M));            // K is built (and earlier users of the buffers are done) before S/S2 start
     GPK_CUDA(h, cudaStreamWaitEvent(S, ev, 0));
     GPK_CUDA(h, cudaStreamWaitEvent(S2, ev, 0));
-    GPK_CUDA(h, cudaStreamWaitEvent(S3, ev, 0));
+    if (Kinv) GPK_CUDA(h, cudaStreamWaitEvent(S3, ev, 0));   // (a stream that is forked must also be joined: graph capture insists)
     cudaEvent_t evGcol_prev = nullptr;              // S finished block column k+1 of trailing update k-1
     cudaEvent_t evLi = nullptr;                     // S2 finished the last row of L^-1
     int rc;
@@ -352,11 +352,8 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     // alpha = L^-t L^-1 y and the log-likelihood overlap it.
     cudaEvent_t e1 = next_event(h), e2 = next_event(h);
     GPK_CUDA(h, cudaEventRecord(e1, S));
-    GPK_CUDA(h, cudaEventRecord(e2, S3));
     GPK_CUDA(h, cudaStreamWaitEvent(M, e1, 0));
-    if (!Kinv) {                                   // no K^-1 requested: S3 idle, join the row chain
-        GPK_CUDA(h, cudaEventRecord(e2, S2));
-    }
+    GPK_CUDA(h, cudaEventRecord(e2, Kinv ? S3 : S2));   // no K^-1 requested: S3 was never forked, join the row chain
     if (kinv_done && Kinv && evLi) {
         GPK_CUDA(h, cudaStreamWaitEvent(M, evLi, 0));
         *kinv_done = e2;

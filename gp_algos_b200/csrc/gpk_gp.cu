@@ -10,56 +10,6 @@
 #include <stdlib.h>
 
 #include <new>
-#include <utility>
-#include <vector>
-
-// ------------------------------------------------------------------------------------------------------------------
-// CUDA-graph replay of the single-problem evaluation.  One logLikelihoodWithDerivatives call at n = 8192 is ~350 kernel
-// launches plus ~300 event records / waits on 8 streams; an optimiser (GpPredictor.scala:126-142 -> Optimization.scala:30-61)
-// repeats exactly that launch sequence 25-60 times with new hyper-parameters.  The second call with one signature
-// (same device buffers, shape and workspace) is stream-captured, instantiated once and replayed from then on, so a
-// call costs the host two launches -- the throughput no longer depends on how fast (or how contended: 8 ranks on one
-// box) the host thread enqueues.  Hyper-parameters reach the kernels through a ProblemParams record in device memory
-// that a one-thread kernel rewrites in front of every replay, so the graph itself never changes.
-// ------------------------------------------------------------------------------------------------------------------
-struct gpk_capture_log {
-    std::vector<std::pair<cudaGraphNode_t, int>> nodes;   // kernel node, priority of the stream it was launched on
-};
-struct gpk_eval_graph {
-    const double* dX; const double* dy; double* out; int* info;   // signature of the captured call
-    int n, D, nparams, family; int64_t ldx; unsigned arena_epoch;
-    int calls;               // eager calls seen with this signature
-    int failed;              // capture was refused once: stay eager
-    cudaGraphExec_t exec;    // null until captured
-    int kernels;             // kernel nodes per replay (gpk_launch_count)
-};
-
-void gpk_capture_note(gpk_handle h) {
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    const cudaGraphNode_t* deps = nullptr;
-    size_t nd = 0;
-    if (cudaStreamGetCaptureInfo(h->stream, &st, nullptr, nullptr, &deps, &nd) != cudaSuccess) { cudaGetLastError(); return; }
-    if (st != cudaStreamCaptureStatusActive || nd != 1) return;   // right after a launch the stream depends on exactly that node
-    // stream classes: 0 main (the spine), 1 side (forked GEMMs of a recursion node), 2.. the look-ahead driver's bulk streams
-    int cls = 0;
-    for (int i = 0; i < GPK_NSIDE; ++i) if (h->stream == h->side[i]) cls = 1;
-    for (int i = 0; i < GPK_NPIPE; ++i) if (h->stream == h->pipe[i]) cls = 2 + i;
-    int prio = cls == 0 ? h->prio_main : cls == 1 ? h->prio_side : h->prio_pipe;
-    static int over[2 + GPK_NPIPE], have = -1;
-    if (have < 0) {   // GPK_GRAPH_PRIO="main,side,pipe0,pipe1,pipe2" (tuning aid)
-        const char* e = getenv("GPK_GRAPH_PRIO");
-        have = e && sscanf(e, "%d,%d,%d,%d,%d", &over[0], &over[1], &over[2], &over[3], &over[4]) == 5;
-    }
-    if (have) prio = over[cls];
-    h->cap->nodes.emplace_back(deps[0], prio);
-}
-
-void gpk_eval_graph_drop(gpk_handle h) {
-    if (!h || !h->eval_graph) return;
-    if (h->eval_graph->exec) cudaGraphExecDestroy(h->eval_graph->exec);
-    delete h->eval_graph;
-    h->eval_graph = nullptr;
-}
 
 namespace {
 
@@ -202,7 +152,8 @@ __global__ void store_params_kernel(const ProblemParams pp, ProblemParams* __res
     if (threadIdx.x == 0) *dst = pp;
 }
 
-// The single-problem evaluation through the graph cache (see the top of this file).
+// The single-problem evaluation through the graph cache (gpk_graph.cu).  Hyper-parameters reach the kernels through a
+// ProblemParams record in device memory that a one-thread kernel rewrites in front of every replay.
 int nll_grad_single(gpk_handle h, const double* dX, int n, int D, int64_t ldx, const double* dy, const double* theta, int has_s,
                     double s, int nparams, double* out_dev, int* info_dev) {
     if (!h->graph_mode) return nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev);
@@ -210,68 +161,20 @@ int nll_grad_single(gpk_handle h, const double* dX, int n, int D, int64_t ldx, c
     int rc = gpk_make_problem_params(h, theta, D, has_s, s, &pp);
     if (rc) return rc;
     Work w;
-    rc = make_work(h, n, D, 1, &w);     // sizes every arena now, so that the epoch below is final
+    rc = make_work(h, n, D, 1, &w);     // sizes every arena now, so that the workspace epoch the cache compares is final
     if (rc) return rc;
     if (nparams > 0 && gpk_use_pipelined(w.N, 1) && !gpk_arena(h, ARENA_KINV, (size_t)w.N * w.N * sizeof(double))) return GPK_ENOMEM;
-    gpk_eval_graph* g = h->eval_graph;
-    if (!g || g->dX != dX || g->dy != dy || g->out != out_dev || g->info != info_dev || g->n != n || g->D != D ||
-        g->nparams != nparams || g->ldx != ldx || g->arena_epoch != h->arena_epoch || g->family != h->kernel_family) {
-        gpk_eval_graph_drop(h);
-        g = new (std::nothrow) gpk_eval_graph();
-        if (!g) return gpk_set_error(h, GPK_ENOMEM, "host allocation failed");
-        memset(g, 0, sizeof(*g));
-        g->dX = dX; g->dy = dy; g->out = out_dev; g->info = info_dev; g->n = n; g->D = D; g->nparams = nparams; g->ldx = ldx; g->family = h->kernel_family;
-        g->arena_epoch = h->arena_epoch;
-        h->eval_graph = g;
-    }
+    GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.p[0] = dX; key.p[1] = dy; key.p[2] = out_dev; key.p[3] = info_dev;
+    key.i[0] = n; key.i[1] = D; key.i[2] = nparams; key.i[3] = ldx; key.i[4] = h->kernel_family;
     store_params_kernel<<<1, 32, 0, h->stream>>>(pp, w.pp_dev);
     GPK_LAUNCH_CHECK(h);
-    if (g->exec) {
-        GPK_CUDA(h, cudaGraphLaunch(g->exec, h->stream));
-        h->launches += g->kernels;
-        return GPK_OK;
-    }
-    if (g->failed || g->calls++ == 0)   // first call with this signature: eager (it also sizes the workspace and sets kernel attributes)
-        return nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev, &pp);
-    // second call: record the same launch sequence instead of running it
-    gpk_capture_log log;
-    const int64_t l0 = h->launches;
-    GPK_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    h->cap = &log;
-    rc = nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev, &pp);
-    h->cap = nullptr;
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-    const int kernels = (int)(h->launches - l0);
-    h->launches = l0;
-    if (rc == GPK_OK && ce == cudaSuccess && graph) {
-        for (auto& nd : log.nodes) {          // keep the streams' priorities: the look-ahead spine must overtake the bulk updates
-            cudaLaunchAttributeValue v;
-            memset(&v, 0, sizeof(v));
-            v.priority = nd.second;
-            if (cudaGraphKernelNodeSetAttribute(nd.first, cudaLaunchAttributePriority, &v) != cudaSuccess) cudaGetLastError();
-        }
-        // without this flag every node runs at the priority of the stream the graph is launched into
-        ce = cudaGraphInstantiate(&g->exec, graph, cudaGraphInstantiateFlagUseNodePriority);
-    }
-    if (graph) cudaGraphDestroy(graph);
-    if (rc != GPK_OK || ce != cudaSuccess || !g->exec) {
-        cudaGetLastError();
-        g->exec = nullptr;
-        g->failed = 1;
-        if (getenv("GPK_GRAPH_DEBUG")) fprintf(stderr, "[gpk] graph capture refused (rc %d, %s): staying eager\n", rc, cudaGetErrorString(ce));
-        return nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev, &pp);
-    }
-    g->kernels = kernels;
-    if (getenv("GPK_GRAPH_DEBUG")) {
-        int least = 0, greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        fprintf(stderr, "[gpk] evaluation captured: %d kernel nodes (%zu with a priority; handle priorities main %d side %d bulk %d, "
-                "device range %d..%d)\n", kernels, log.nodes.size(), h->prio_main, h->prio_side, h->prio_pipe, greatest, least);
-    }
-    GPK_CUDA(h, cudaGraphLaunch(g->exec, h->stream));
-    h->launches += g->kernels;
-    return GPK_OK;
+    auto body = [&]() { return nll_grad_core(h, 1, dX, n, D, ldx, 0, dy, theta, has_s, s, nparams, out_dev, info_dev, &pp); };
+    // captured on the second call: an optimiser's objective is called 25-60 times per fit, a benchmark loop more often
+    static int after = -1;
+    if (after < 0) { const char* e = getenv("GPK_GRAPH_AFTER_EVAL"); after = e ? atoi(e) : 1; if (after < 1) after = 1; }
+    return gpk_graph_run(h, GPK_SLOT_EVAL, key, after, body, "evaluation");
 }
 
 

@@ -36,14 +36,25 @@ struct gpk_handle_s {
     // optimiser calls it over and over with the same buffers and new hyper-parameters)
     int graph_mode;               // 0 off, 1 capture on the second call with one signature and replay from then on
     unsigned arena_epoch;         // bumped whenever an arena is (re)allocated: a cached graph holds arena pointers
-    struct gpk_eval_graph* eval_graph;
+    struct gpk_graph_slot* slots[2];   // cached graphs (gpk_graph.cu): GPK_SLOT_EVAL, GPK_SLOT_EP_SWEEP
     struct gpk_capture_log* cap;  // non-null while capturing: every kernel node with the priority of the stream it came from
     int prio_main, prio_side, prio_pipe;
     int kernel_family;            // gpk_kernel_family: how (D, theta) arguments are interpreted
     char err[512];
 };
-void gpk_capture_note(gpk_handle h);    // gpk_gp.cu
-void gpk_eval_graph_drop(gpk_handle h); // gpk_gp.cu: forget the cached graph (handle teardown)
+// ---- graph replay (gpk_graph.cu) ----
+#define GPK_NSLOTS 2
+enum { GPK_SLOT_EVAL = 0, GPK_SLOT_EP_SWEEP = 1 };
+struct GraphKey { const void* p[6]; int64_t i[6]; };   // zero-initialise, then fill: compared bytewise
+void gpk_capture_note(gpk_handle h);
+void gpk_graph_drop_all(gpk_handle h);                  // forget every cached graph (handle teardown, graph mode off)
+// Runs `body` (a launch sequence on h->stream that forks/joins the handle's other streams and synchronises nothing) eagerly on
+// the first call with `key`, captures it on the second and replays the instantiated graph afterwards.
+int gpk_graph_run_impl(gpk_handle h, int slot, const GraphKey& key, int eager_calls, int (*body)(void*), void* ctx, const char* what);
+template <class F>
+int gpk_graph_run(gpk_handle h, int slot, const GraphKey& key, int eager_calls, F& body, const char* what) {
+    return gpk_graph_run_impl(h, slot, key, eager_calls, [](void* c) { return (*static_cast<F*>(c))(); }, &body, what);
+}
 
 enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7, ARENA_PP = 8, ARENA_INFO = 9, ARENA_GEMV = 10, ARENA_KINV = 11, GPK_NARENA = 12 };
 

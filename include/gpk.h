@@ -51,10 +51,12 @@ int gpk_synchronize(gpk_handle h);
 /* number of kernel launches issued through this handle since creation (bench.py "gpu_launches") */
 int64_t gpk_launch_count(gpk_handle h);
 const char* gpk_version(void);
-/* Repeated gpk_gp_nll_grad[_dev] calls with the same buffers and shape (an optimiser's objective,
- * GpPredictor.scala:126-142) are captured into a CUDA graph on the second call and replayed afterwards; new
- * hyper-parameters reach the replay through device memory.  on = 0 keeps every call on eager launches
- * (default 1, or the GPK_GRAPH environment variable).  Results are identical either way. */
+/* Launch sequences that callers repeat verbatim are captured into CUDA graphs and replayed: the single-problem
+ * gpk_gp_nll_grad[_dev] evaluation (an optimiser's objective, GpPredictor.scala:126-142; same buffers and shape, new
+ * hyper-parameters through device memory) from its second call on, and the EP sweep (EpParameterEstimator.scala:37-67) once
+ * ~30 sweeps of one size have run on the handle (capturing costs about one sweep).  on = 0: eager launches only; 1 (default,
+ * or the GPK_GRAPH environment variable): as described; 2: capture at the first repetition of anything.  Results are
+ * bit-identical in every mode. */
 int gpk_set_graph_mode(gpk_handle h, int on);
 
 /* ---- kernel family -------------------------------------------------------------------------------

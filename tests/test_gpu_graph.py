@@ -109,3 +109,28 @@ def test_other_entry_points_between_replays():
     again = p.logLikelihoodWithDerivatives(inp, theta0, 10)
     assert again[0] == ref[0] and np.array_equal(again[1], ref[1])
     h.close()
+
+
+def test_ep_sweep_replay_equals_eager():
+    """EpParameterEstimator.estimateSiteParams (EpParameterEstimator.scala:29-69): sweep 1 eager, sweep 2 captured, later sweeps
+    replayed (graph mode 2) -- same site parameters, factor and log Z bit for bit as on a handle that never captures, and the
+    oracle's to 1e-9.  n = 4200 goes through the look-ahead factorisation inside the sweep."""
+    for n, sweeps in ((300, 5), (4200, 4)):
+        X, t, th = synthetic.make_c3(n=n, D=4)
+        kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
+        hg, he = _lib.Handle(0), _lib.Handle(0)
+        hg.set_graph_mode(2)
+        he.set_graph_mode(0)
+        K = gp.MatrixUtils.buildKernelMatrix(kf, X, handle=he)
+        sg, Lg = gp.EpParameterEstimator(K, t, gp.FixedSweeps(sweeps), hg).estimateSiteParams
+        se, Le = gp.EpParameterEstimator(K, t, gp.FixedSweeps(sweeps), he).estimateSiteParams
+        assert np.array_equal(sg.tauSiteParams, se.tauSiteParams) and np.array_equal(sg.niSiteParams, se.niSiteParams)
+        assert sg.marginalLogLikelihood == se.marginalLogLikelihood and np.array_equal(Lg, Le)
+        # a second run on the same handle starts from the cached graph
+        sg2, _ = gp.EpParameterEstimator(K, t, gp.FixedSweeps(sweeps), hg).estimateSiteParams
+        assert np.array_equal(sg2.tauSiteParams, se.tauSiteParams) and sg2.marginalLogLikelihood == se.marginalLogLikelihood
+        if n <= 400:
+            o = orc.lit_ep_estimate(K, t, fixed_sweeps=sweeps)
+            assert np.all(np.abs(sg.tauSiteParams - o["tau"]) <= RTOL * np.abs(o["tau"]).max())
+            assert abs(sg.marginalLogLikelihood - o["logZ"]) <= RTOL * abs(o["logZ"])
+        hg.close(); he.close()

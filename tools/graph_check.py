@@ -30,8 +30,13 @@ for n in [int(v) for v in os.environ.get("GRAPH_NS", "700,8192").split(",")]:
             h.check(h.lib.gpk_gp_nll_grad_dev(h.h, dX.data_ptr(), n, D, n, dy.data_ptr(), _lib.ptr(th), 0, 0.0, P,
                                               dout.data_ptr(), dinfo.data_ptr()))
         outs = []
-        for th in thetas:
+        for i, th in enumerate(thetas):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
             ev(th)
+            torch.cuda.synchronize()
+            if i < 3:   # graph mode: eager, capture + instantiate + launch, replay
+                print(f"n={n} graph={mode}: call {i + 1} took {1e3 * (time.perf_counter() - t0):8.2f} ms wall", flush=True)
             outs.append(dout.cpu().numpy().copy())
         res[mode] = np.array(outs)
         for _ in range(3):
