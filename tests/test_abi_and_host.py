@@ -160,3 +160,28 @@ def test_product_and_tools_never_import_the_oracle():
     gpu_arm = bench[bench.index("def run_gpk"):]
     head, tail = gpu_arm.split("t_cpu = cpu_eval_time", 1)
     assert "oracle" not in head.replace("oracle/ is imported by the cpu_baseline", "").replace("oracle LAPACK", "")
+
+
+def test_ctypes_bindings_match_the_header_prototypes():
+    """Every entry point the Python mirror calls is declared in include/gpk.h, and its argtypes list has exactly as many
+    entries as the C prototype has parameters (a drifted binding would pass garbage through the ABI silently)."""
+    hdr = open(os.path.join(ROOT, "include", "gpk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|int64_t|const char\s*\*)\s+(gpk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    assert len(protos) >= 40
+    lib = _lib.load()
+    bound = 0
+    for name, nargs in protos.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue
+        bound += 1
+        assert len(fn.argtypes) == nargs, f"{name}: {len(fn.argtypes)} argtypes bound, {nargs} parameters in include/gpk.h"
+    assert bound >= 35
+    # and the other direction: nothing is bound that the header does not declare
+    src = open(os.path.join(ROOT, "gp_algos_b200", "_lib.py")).read()
+    for name in set(re.findall(r"lib\.(gpk_[a-z0-9_]+)\.", src)):
+        assert name in protos, f"{name} bound in _lib.py but not declared in include/gpk.h"
