@@ -550,7 +550,7 @@ void orc_ep_classify(const double *K, int n, const double *Ks, int m, const doub
                      double *fmean_out, double *fvar_diag_out)
 {
     double *st = (double *)malloc(sizeof(double) * (size_t)n);
-    double *rhs = (double *)malloc(sizeof(double) * (size_t)n);
+    double *rhs = (double *)calloc((size_t)n, sizeof(double));
     double *t1 = (double *)malloc(sizeof(double) * (size_t)n);
     double *z = (double *)malloc(sizeof(double) * (size_t)n);
     double *rhs1 = (double *)malloc(sizeof(double) * (size_t)n * m);
