@@ -185,3 +185,22 @@ def test_ctypes_bindings_match_the_header_prototypes():
     src = open(os.path.join(ROOT, "gp_algos_b200", "_lib.py")).read()
     for name in set(re.findall(r"lib\.(gpk_[a-z0-9_]+)\.", src)):
         assert name in protos, f"{name} bound in _lib.py but not declared in include/gpk.h"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/gpk.h is the drop-in boundary for JNA / JNI / cgo-style bindings: it must compile as C99 (no C++ types) and a
+    plain C program must link against libgpk.so.  Without a GPU gpk_create fails cleanly (no CPU fallback), with one it succeeds."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "gpk.h"\n#include <stdio.h>\n'
+                   "int main(void) { gpk_handle h = 0; int rc = gpk_create(&h, 0, 0);\n"
+                   '  printf("%d %s\\n", rc, gpk_version()); if (rc == GPK_OK) gpk_destroy(h); return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.lib_path())
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-o", str(exe), "-L", libdir, "-lgpk", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    rc, version = out.stdout.split(" ", 1)
+    assert "sm_100a" in version
+    assert int(rc) == (0 if _have_gpu() else _lib.GPK_ECUDA)
