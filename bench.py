@@ -49,7 +49,10 @@ def config(n, n_gpus):
                         f"synthetic seed 2 (SURVEY.md 8(d))",
             "n": n, "D": DIM, "nparams": NPARAMS,
             "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} independent MLE restarts, one per GPU, no collective",
-            "l2": "working set (K, L^-1: 2 x 512 MiB) exceeds the 126 MB L2; no explicit flush"}
+            "l2": "working set (K, L^-1: 2 x 512 MiB) exceeds the 126 MB L2; no explicit flush",
+            "launches": ("eager launches (GPK_GRAPH=0)" if os.environ.get("GPK_GRAPH", "1") == "0" else
+                         "CUDA-graph replay: per step one parameter kernel + one graph launch; gpu_launches counts the graph's "
+                         "kernel nodes (398 per evaluation), captured during warm-up")}
 
 
 # ------------------------------------------------------------------------------------------------------
