@@ -14,6 +14,10 @@
  * "PARITY UNPINNED" by the reference; it is defended instead by an mpmath 50-digit arbiter,
  * finite-difference gradient checks and a literal-vs-LAPACK cross-check (tests/).
  *
+ * The reference's second closed-form kernel, Co2Kernel (gp/regression/Co2Prediction.scala:29-137), is restated further down;
+ * its only pin from the reference is the shipped output src/main/resources/co2/co2PredResults.txt (soft, ~1e-4 relative on the
+ * training range; tests/test_co2_oracle_and_host.py), everything else about it is "parity unpinned" as well.
+ *
  * Third-party arithmetic that is NOT in /root/reference and is restated here:
  *   - Breeze 0.8.1 `cholesky`  -> LAPACK dpotrf('L') : unblocked dpotf2 recurrence below.
  *   - Breeze `*`, `trace`, `dot` -> plain ascending-index dot products.

@@ -18,7 +18,8 @@ reference's own tests pin (checked in tests/test_oracle_pins.py) and what is "pa
 
 Reference citations are relative to /root/reference/src/main/scala/:
 KR = utils/KernelRequisites.scala, MU = utils/MatrixUtils.scala, GPP = gp/regression/GpPredictor.scala,
-EP = gp/classification/EpParameterEstimator.scala, GPC = gp/classification/GpClassifier.scala.
+EP = gp/classification/EpParameterEstimator.scala, GPC = gp/classification/GpClassifier.scala,
+Co2 = gp/regression/Co2Prediction.scala (second kernel family, `with co2_kernel():`).
 """
 from __future__ import annotations
 
