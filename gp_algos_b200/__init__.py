@@ -7,6 +7,7 @@ and error behaviour), used by the parity tests and the benchmark:
     utils.KernelRequisites  ->  gp_algos_b200.kernel_requisites  (GaussianRbfParams, GaussianRbfKernel)
     gp.regression.Co2Prediction -> gp_algos_b200.co2_prediction  (Co2HyperParams, Co2Kernel: the second closed-form kernel)
     utils.MatrixUtils       ->  gp_algos_b200.matrix_utils       (buildKernelMatrix, forwardSolve, ...)
+    utils.StatsUtils        ->  gp_algos_b200.stats_utils        (host helpers of the callers: pnorm, mse, meanAndVarOfData, ...)
     gp.regression.GpPredictor -> gp_algos_b200.gp_predictor      (GpPredictor, PredictionInput, ...)
     gp.classification.*      ->  gp_algos_b200.ep_classification (EpParameterEstimator, GpClassifier, ...)
     dynamicalsystems.filtering.{UnscentedKalmanFilter, GPUnscentedKalmanFilter} -> gp_algos_b200.gp_ukf
@@ -22,6 +23,7 @@ from .co2_prediction import Co2HyperParams, Co2Kernel, co2DataToYearWithValue  #
 from .gp_predictor import GpPredictor, PredictionInput, PredictionTrainingInput, GaussianDistribution  # noqa: F401
 from . import matrix_utils as MatrixUtils  # noqa: F401
 from . import batched  # noqa: F401
+from . import stats_utils as StatsUtils  # noqa: F401
 from .ep_classification import (EpParameterEstimator, GpClassifier, MarginalLikelihoodEvaluator, SiteParams,  # noqa: F401
                                 AvgBasedStopCriterion, FixedSweeps, ClassifierInput, AfterEstimationClassifierInput,
                                 HyperParameterOptimInput, GradientHyperParamsOptimizer, ApacheCommonsOptimizer,
