@@ -11,6 +11,7 @@ and error behaviour), used by the parity tests and the benchmark:
     gp.regression.GpPredictor -> gp_algos_b200.gp_predictor      (GpPredictor, PredictionInput, ...)
     gp.classification.*      ->  gp_algos_b200.ep_classification (EpParameterEstimator, GpClassifier, ...)
     dynamicalsystems.filtering.{UnscentedKalmanFilter, GPUnscentedKalmanFilter} -> gp_algos_b200.gp_ukf
+    dynamicalsystems.filtering.{SsmExamples, SsmModel.generateSeries} -> gp_algos_b200.ssm_examples (host: test models + sampler)
     gp.optimization.GPOptimizer -> gp_algos_b200.gp_optimizer    (GP-UCB inner loop on a resident model)
     (batched independent GPs and their rank sharding: gp_algos_b200.batched;
      one large GP over a 2-D block-cyclic GPU grid: gp_algos_b200.distributed)
@@ -24,6 +25,7 @@ from .gp_predictor import GpPredictor, PredictionInput, PredictionTrainingInput,
 from . import matrix_utils as MatrixUtils  # noqa: F401
 from . import batched  # noqa: F401
 from . import stats_utils as StatsUtils  # noqa: F401
+from . import ssm_examples as SsmExamples  # noqa: F401
 from .ep_classification import (EpParameterEstimator, GpClassifier, MarginalLikelihoodEvaluator, SiteParams,  # noqa: F401
                                 AvgBasedStopCriterion, FixedSweeps, ClassifierInput, AfterEstimationClassifierInput,
                                 HyperParameterOptimInput, GradientHyperParamsOptimizer, ApacheCommonsOptimizer,

@@ -53,3 +53,47 @@ def test_ukf_on_a_linear_gaussian_model_is_the_kalman_filter():
         assert np.allclose(out.hiddenMeans[:, t], mq + Kq @ (y[:, t] - H @ mq), rtol=1e-9, atol=1e-12)
     assert out.logLikelihood is not None and np.isfinite(out.logLikelihood)
     assert np.isfinite(nllOfHiddenData(z, out.hiddenMeans, out.hiddenCovs))
+
+
+# ---- the facts the reference's own src/test/scala/dynamicalsystems/filtering/UnscentedKalmanFilterTest.scala holds -----------
+def test_reference_unscented_transform_facts():
+    ukf = gp.UnscentedKalmanFilter()
+    # :44-56  1-d Gaussian through the identity
+    tr = ukf.unscentedTransform(gp.GaussianDistribution(np.array([2.]), np.array([[2.]])), gp.UnscentedTransformParams(), lambda pts: pts)
+    assert tr.distribution.dim == 1 and tr.distribution.sigma[0, 0] != 0.0
+    assert tr.sigmaPoints.shape[0] == 3 and tr.transformedSigmaPoints.shape[0] == 3
+    assert np.array_equal(tr.transformedSigmaPoints, tr.sigmaPoints)
+    assert abs(tr.distribution.mean[0] - 2.0) < 1e-14 and abs(tr.distribution.sigma[0, 0] - 2.0) < 1e-14   # identity keeps the moments
+    # :58-71  3-d Gaussian through the elementwise square
+    g3 = gp.GaussianDistribution(np.array([1., 2., 3.]), np.eye(3))
+    tr = ukf.unscentedTransform(g3, gp.UnscentedTransformParams(), lambda pts: pts * pts)
+    assert tr.distribution.dim == 3 and tr.distribution.sigma.shape == (3, 3)
+    assert tr.sigmaPoints.shape[0] == 7 and tr.transformedSigmaPoints.shape[0] == 7
+    np.linalg.cholesky(tr.distribution.sigma)                                       # `cholesky(transformedDistr.sigma)` must not throw
+    assert np.allclose(tr.distribution.mean, np.array([1., 4., 9.]) + 1.0, rtol=1e-13)   # E[x^2] = mu^2 + sigma^2, exact for the UT
+
+
+def test_reference_filter_facts_on_the_sinusoidal_and_kitagawa_models():
+    from gp_algos_b200.ssm_examples import SinusoidalSsm, KitagawaSsm, generateSeries
+    rng = np.random.default_rng(11)
+    seq = 50
+    cases = ((SinusoidalSsm(), gp.GaussianDistribution(np.array([0.]), np.array([[1.]]))),          # GaussianDistribution.standard (:29)
+             (KitagawaSsm(), gp.GaussianDistribution(np.array([0.]), np.array([[0.5 * 0.5]]))))     # initHiddenStateDistrKit (:30-31)
+    for model, init in cases:
+        hidden, obs = generateSeries(model, seq, init, rng)
+        assert hidden.shape == (1, seq) and obs.shape == (1, seq)
+        inp = gp.UnscentedFilteringInput(model, obs, None, init.mean, init.sigma, lambda ctx, m=model: m.latentNoise,
+                                         lambda ctx, m=model: m.obsNoise)
+        for params in (gp.UnscentedTransformParams(alpha=1.0), gp.UnscentedTransformParams(2.012, 0.24, 0.4871)):   # :82-86, :97-99
+            out = gp.UnscentedKalmanFilter().inferHiddenState(inp, params, True)
+            assert out.hiddenMeans.shape[1] == seq and out.hiddenMeans.shape[0] == hidden.shape[0] and len(out.hiddenCovs) == seq
+            assert np.all(np.isfinite(out.hiddenMeans))
+            # (the reference asserts shapes only: on the bimodal Kitagawa model the filter may lose track and the likelihood,
+            #  log of an underflowed density as in StatsUtils.scala:57-59, is then -inf)
+            assert model is cases[1][0] or np.isfinite(out.logLikelihood)
+    # the sinusoidal model is easy: the filter tracks the hidden state better than the prior mean does
+    model, init = cases[0]
+    hidden, obs = generateSeries(model, 200, init, np.random.default_rng(12))
+    inp = gp.UnscentedFilteringInput(model, obs, None, init.mean, init.sigma, lambda ctx: model.latentNoise, lambda ctx: model.obsNoise)
+    out = gp.UnscentedKalmanFilter().inferHiddenState(inp, gp.UnscentedTransformParams(alpha=1.0), True)
+    assert gp.StatsUtils.mse(out.hiddenMeans[:, 1:].T, hidden[:, 1:].T) < gp.StatsUtils.mse(np.zeros_like(hidden[:, 1:].T), hidden[:, 1:].T)
