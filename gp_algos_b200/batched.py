@@ -93,3 +93,119 @@ def sharded_map(B: int, local_eval: Callable[[int, int], Sequence[np.ndarray]], 
     dist.all_gather_object(gathered, mine, group=group)
     parts = [g for g in gathered if g is not None]
     return tuple(np.concatenate([p[k] for p in parts], axis=0) for k in range(len(parts[0])))
+
+
+# ---- MLE restarts in lockstep ----------------------------------------------------------------------------------------------
+class LockstepLbfgs:
+    """R independent L-BFGS(m = 4, maxIter) minimisations advanced in lockstep: in every round each live instance proposes ONE
+    point and all proposals are evaluated by ONE call of `batched_func(points[R', P], which[R']) -> (values[R'], grads[R', P])`
+    -- for MLE restarts that is one gpk_gp_nll_grad_batched launch sequence for all restarts instead of R sequential
+    evaluations (GPOptimizer.scala:54-61 and the `obtainOptimalHyperParams` callers restart sequentially).  Per instance the
+    algorithm and the wrapper logic are those of BreezeLbfgsOptimizer (optimization/Optimization.scala:37-61: best-seen point,
+    one extra evaluation at the end); a non-finite value (failed factorisation) is treated as a rejected line-search step."""
+
+    def __init__(self, maxIter: int = 20, m: int = 4, c1: float = 1e-4, maxLineSearch: int = 20):
+        self.maxIter, self.m, self.c1, self.maxLineSearch = maxIter, m, c1, maxLineSearch
+        self.rounds = 0
+        self.evaluations = 0
+
+    def minimize(self, batched_func, initPoints):
+        X0 = np.array(initPoints, dtype=np.float64, copy=True)
+        R, P = X0.shape
+        st = [dict(x=X0[r].copy(), f=None, g=None, hist=[], d=None, slope=None, step=None, ls=0, it=0, phase="init",
+                   trial=X0[r].copy(), best_x=X0[r].copy(), best_v=np.finfo(float).max) for r in range(R)]
+
+        def direction(s):
+            g, hist = s["g"], s["hist"]
+            q = g.copy()
+            alphas = []
+            for sv, yv in reversed(hist):
+                a = (sv @ q) / (sv @ yv)
+                alphas.append(a)
+                q -= a * yv
+            if hist:
+                sv, yv = hist[-1]
+                q *= (sv @ yv) / (yv @ yv)
+            for (sv, yv), a in zip(hist, reversed(alphas)):
+                b = (yv @ q) / (sv @ yv)
+                q += (a - b) * sv
+            d = -q
+            slope = float(g @ d)
+            if not slope < 0:                                        # not a descent direction: restart from steepest descent
+                s["hist"] = []
+                d, slope = -g, -float(g @ g)
+            s["d"], s["slope"] = d, slope
+            s["step"] = 1.0 if s["hist"] else 1.0 / max(1.0, float(np.sqrt(g @ g)))
+            s["ls"] = 0
+            s["trial"] = s["x"] + s["step"] * d
+
+        while True:
+            live = [r for r in range(R) if st[r]["phase"] != "done"]
+            if not live:
+                break
+            pts = np.stack([st[r]["trial"] for r in live])
+            vals, grads = batched_func(pts, np.array(live))
+            self.rounds += 1
+            self.evaluations += len(live)
+            for j, r in enumerate(live):
+                s = st[r]
+                v, g = float(vals[j]), np.asarray(grads[j], dtype=np.float64)
+                if np.isfinite(v) and v < s["best_v"]:               # Optimization.scala:44-46
+                    s["best_v"], s["best_x"] = v, s["trial"].copy()
+                if s["phase"] == "final":                            # :52-55
+                    s["result"] = s["trial"] if (np.isfinite(v) and v < s["best_v"]) else s["best_x"]
+                    s["phase"] = "done"
+                    continue
+                if s["phase"] == "init":
+                    if not np.isfinite(v):
+                        s["result"], s["phase"] = s["x"], "done"
+                        continue
+                    s["f"], s["g"] = v, g
+                    accepted = True
+                else:
+                    accepted = np.isfinite(v) and v <= s["f"] + self.c1 * s["step"] * s["slope"]
+                    if accepted:
+                        sv, yv = s["trial"] - s["x"], g - s["g"]
+                        if sv @ yv > 1e-12 * np.sqrt((sv @ sv) * (yv @ yv)):
+                            s["hist"].append((sv, yv))
+                            s["hist"] = s["hist"][-self.m:]
+                        s["x"], s["f"], s["g"] = s["trial"].copy(), v, g
+                        s["it"] += 1
+                    else:
+                        s["ls"] += 1
+                        s["step"] *= 0.5
+                        if s["ls"] < self.maxLineSearch:
+                            s["trial"] = s["x"] + s["step"] * s["d"]
+                            continue
+                if (not accepted or s["it"] >= self.maxIter
+                        or np.sqrt(s["g"] @ s["g"]) <= 1e-9 * max(1.0, abs(s["f"]))):
+                    s["phase"], s["trial"] = "final", s["x"].copy()  # the wrapper's extra evaluation at the end point
+                    continue
+                s["phase"] = "search"
+                direction(s)
+        return np.stack([s["result"] for s in st]), np.array([s["best_v"] for s in st])
+
+    def maximize(self, batched_func, initPoints):
+        def minus(p, which):
+            v, g = batched_func(p, which)
+            return -np.asarray(v, dtype=np.float64), -np.asarray(g, dtype=np.float64)
+        pts, best = self.minimize(minus, initPoints)
+        return pts, -best
+
+
+def obtain_optimal_hyper_params_multistart(trainingData, targets, initThetas, sigmaNoise=None, maxIter: int = 20, handle=None):
+    """GpPredictor.obtainOptimalHyperParams (GpPredictor.scala:126-142, optimizeNoise = true) from R start points at once: the
+    restarts share the training set (strideX = 0) and every lockstep round is ONE batched objective+gradient call.
+    Returns (thetas[R, D+2], logLikelihood[R]) -- the best-seen point and value of every restart."""
+    X = np.asarray(trainingData, dtype=np.float64)
+    y = np.ascontiguousarray(targets, dtype=np.float64)
+    init = np.atleast_2d(np.asarray(initThetas, dtype=np.float64))
+    if init.shape[1] != X.shape[1] + 2:
+        raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, f"requirement failed: {init.shape[1]} does not equal to {X.shape[1] + 2}")
+
+    def objective(points, which):
+        ll, grad, info = log_likelihood_with_derivatives_batched(X, np.tile(y, (len(points), 1)), points, sigmaNoise, handle=handle)
+        ll = np.where(info == 0, ll, -np.inf)                        # a restart whose K is not positive definite backs off
+        return ll, grad
+
+    return LockstepLbfgs(maxIter=maxIter).maximize(objective, init)
