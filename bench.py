@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--impl", default="gpk", choices=["gpk", "reference"])
     ap.add_argument("--n", type=int, default=N_TRAIN, help="(debug only) problem size; the reported config is n=8192")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the C4 / C5 sharded record (debug)")
     return ap.parse_args()
 
 
@@ -77,11 +78,26 @@ def cpu_literal_time(n=768):
     return time.perf_counter() - t0
 
 
+def blas_threads_all():
+    """Give the CPU arm every host core, whatever the launcher exported: torch.distributed.run sets OMP_NUM_THREADS=1 for
+    its workers, which throttled the round-1 reference arm at N >= 2 to one BLAS thread.  Returns the thread count in use."""
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits, threadpool_info
+        import numpy  # noqa: F401  (loads OpenBLAS so that threadpoolctl sees it)
+        import scipy.linalg  # noqa: F401
+        threadpool_limits(limits=cores)
+        used = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(used) if used else cores
+    except Exception:
+        return cores
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = blas_threads_all()
     n = args.n
     for _ in range(min(args.warmup, 1)):  # one warm-up eval is enough to page in BLAS (each takes seconds)
         cpu_eval_time(n)
@@ -138,6 +154,235 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+
+# ------------------------------------------------------------------------------------------------------
+# second half of the metric: "Cholesky TFLOP/s vs peak" -- gpk_potrf_lower_dev alone at n = 8192
+# ------------------------------------------------------------------------------------------------------
+def bench_cholesky(h, dX, n, theta, peak_tflops, reps=5):
+    """Factor-only Cholesky (breeze `cholesky` -> dpotrf 'L', GpPredictor.scala:120) of the C2 kernel matrix, resident in HBM.
+    K is rebuilt before every repetition (outside the timed region); algorithmic flops n^3/3."""
+    import numpy as np
+    import torch
+    from gp_algos_b200 import _lib
+    K0 = torch.empty(n * n, dtype=torch.float64, device="cuda")
+    A = torch.empty_like(K0)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    th = np.ascontiguousarray(theta)
+    h.check(h.lib.gpk_cov_se_ard_dev(h.h, dX.data_ptr(), n, DIM, n, _lib.ptr(th), K0.data_ptr(), n))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    for rep in range(reps + 2):
+        A.copy_(K0)
+        torch.cuda.synchronize()
+        e0.record()
+        h.check(h.lib.gpk_potrf_lower_dev(h.h, A.data_ptr(), n, n, info.data_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        if rep >= 2:
+            times.append(e0.elapsed_time(e1))
+    assert int(info.item()) == 0, "factorisation failed"
+    # check: ||L (L^t v) - K v|| / ||K v|| for a random v (three HBM-bound mat-vecs through libgpk)
+    v = torch.from_numpy(np.random.default_rng(7).standard_normal(n)).cuda()
+    t1, t2, t3 = (torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3))
+    h.check(h.lib.gpk_gemv_dev(h.h, 1, n, n, 1.0, A.data_ptr(), n, v.data_ptr(), 0.0, t1.data_ptr()))
+    h.check(h.lib.gpk_gemv_dev(h.h, 0, n, n, 1.0, A.data_ptr(), n, t1.data_ptr(), 0.0, t2.data_ptr()))
+    h.check(h.lib.gpk_gemv_dev(h.h, 0, n, n, 1.0, K0.data_ptr(), n, v.data_ptr(), 0.0, t3.data_ptr()))
+    torch.cuda.synchronize()
+    resid = float(torch.linalg.norm(t2 - t3) / torch.linalg.norm(t3))
+    ms = min(times)
+    tf = float(n) ** 3 / 3 / ms * 1e-9
+    return {"n": n, "ms": ms, "ms_all": times, "tflops": tf, "frac": tf / peak_tflops if peak_tflops else None,
+            "flops": float(n) ** 3 / 3, "what": "gpk_potrf_lower_dev: factor only, K resident in HBM, in place; best of "
+            f"{reps} after 2 warm-ups; frac = tflops / live cuBLAS Dgemm peak", "resid_LLt_v_vs_K_v": resid}
+
+
+# ------------------------------------------------------------------------------------------------------
+# the sharded configs (SURVEY.md 8(e)): C4 = 512 independent GPs split over the ranks, no collective;
+# C5 = one GP of n = 65536 on a 2-D block-cyclic grid with NCCL panel broadcasts
+# ------------------------------------------------------------------------------------------------------
+C4_B, C4_N, C4_M = 512, 1024, 17
+
+
+def _max_over_ranks(dist, vals):
+    import torch
+    t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.tolist()]
+
+
+def bench_c4(h, dist, rank, world, reps=5):
+    """512 x (n = 1024, D = 8) objective+gradient evaluations (MLE-restart flavour, GPOptimizer.scala:54-61 /
+    GPUnscentedKalmanFilter.scala:123-136), problems [lo, hi) = batched.shard_bounds on each rank.  Strong scaling: the total
+    work is fixed.  Device-timed with the shard resident in HBM, and end to end from host buffers."""
+    import numpy as np
+    import torch
+    from gp_algos_b200 import _lib, batched, synthetic
+    lo, hi = batched.shard_bounds(C4_B, rank, world)
+    # rank 0 also times the whole batch alone (the in-run 1-GPU figure the speed-up is quoted against)
+    need = range(C4_B) if rank == 0 else range(lo, hi)
+    probs = {b: synthetic.make_c4_problem(b, n=C4_N, D=DIM, m=C4_M) for b in need}
+
+    def stack(idx):
+        X = np.stack([probs[b][0] for b in idx]); ys = np.stack([probs[b][1] for b in idx]); th = np.stack([probs[b][3] for b in idx])
+        return X, ys, np.ascontiguousarray(th)
+
+    def timed(idx):
+        X, ys, th = stack(idx)
+        nb = len(idx)
+        dX = torch.from_numpy(np.ascontiguousarray(np.transpose(X, (0, 2, 1)))).cuda()
+        dy = torch.from_numpy(ys).cuda()
+        out = torch.zeros(nb * (NPARAMS + 1), dtype=torch.float64, device="cuda")
+        info = torch.zeros(nb, dtype=torch.int32, device="cuda")
+
+        def step():
+            h.check(h.lib.gpk_gp_nll_grad_batched_dev(h.h, nb, dX.data_ptr(), C4_N, DIM, C4_N, C4_N * DIM, dy.data_ptr(), _lib.ptr(th),
+                                                      0, 0.0, NPARAMS, out.data_ptr(), info.data_ptr()))
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        return step, info, out, (X, ys, th)
+
+    step, info, out, host = timed(list(range(lo, hi)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = h.launch_count()
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    launches = (h.launch_count() - l0) // reps
+    assert int(info.abs().sum().item()) == 0, "a C4 problem failed to factor"
+    # end to end: PINNED host buffers in the reference's (Breeze, column-major) layout in, (ll, grad) out through the public
+    # batched API; H2D of X, y and D2H of the results inside the timed region
+    X, ys, th = host
+    Xp = torch.from_numpy(np.ascontiguousarray(np.transpose(X, (0, 2, 1)))).pin_memory()     # (B, D, n): column-major stack
+    yp = torch.from_numpy(ys.copy()).pin_memory()
+    X, ys = Xp.numpy().transpose(0, 2, 1), yp.numpy()
+    batched.log_likelihood_with_derivatives_batched(X, ys, th, handle=h)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    ll, g, _ = batched.log_likelihood_with_derivatives_batched(X, ys, th, handle=h)
+    t_e2e = time.perf_counter() - t0
+    dev = out.cpu().numpy().reshape(hi - lo, NPARAMS + 1)
+    assert np.allclose(dev[:, 0], ll, rtol=1e-12, atol=0) and np.allclose(dev[:, 1:], g, rtol=1e-12, atol=0)
+    ms, t_e2e = _max_over_ranks(dist, [ms, t_e2e])
+    rec = {"workload": f"C4: {C4_B} independent GPs, n={C4_N}, D={DIM}, objective+gradient (P={NPARAMS}); problems split over "
+                       f"{world} GPU(s) by batched.shard_bounds, no data-path collective", "scaling": "strong",
+           "problems_per_s": C4_B / (ms * 1e-3), "ms": ms, "eff_tflops": C4_B * float(C4_N) ** 3 / (ms * 1e-3) * 1e-12,
+           "e2e_problems_per_s": C4_B / t_e2e, "e2e_ms": t_e2e * 1e3, "problems_on_rank0": hi - lo,
+           "e2e_h2d_bytes_rank0": int((hi - lo) * (C4_N * DIM + C4_N) * 8), "e2e_d2h_bytes_rank0": int((hi - lo) * ((NPARAMS + 1) * 8 + 4)),
+           "launches_per_batch_rank0": int(launches), "timing": "CUDA events on each rank's stream, max over ranks"}
+    del step, out, info
+    if world > 1:
+        ms1 = None
+        if rank == 0:
+            step1, info1, out1, _ = timed(list(range(C4_B)))
+            e0.record()
+            for _ in range(reps):
+                step1()
+            e1.record()
+            torch.cuda.synchronize()
+            ms1 = e0.elapsed_time(e1) / reps
+            # the shard's results are bit-identical to the same problems evaluated inside the full batch
+            full = out1.cpu().numpy().reshape(C4_B, NPARAMS + 1)
+            rec["shard_equals_full_batch"] = bool(np.array_equal(full[lo:hi], dev))
+            rec["one_gpu_ms_in_run"] = ms1
+            rec["speedup_vs_one_gpu_in_run"] = ms1 / ms
+        dist.barrier()
+    return rec
+
+
+def bench_c5(dist, rank, world, local, n=65536, nb=1024, reps=2):
+    """One GP of n = 65536, D = 8 (seed 5): K build + 2-D block-cyclic FP64 Cholesky + both solves + log-likelihood
+    (GpPredictor.scala:104-124,144-149) through DistributedGp.fit.  Strong scaling.  CUDA events per rank, max over ranks."""
+    import numpy as np
+    import torch
+    from gp_algos_b200 import synthetic
+    from gp_algos_b200.distributed import DistributedGp, choose_grid
+    X, y, theta = synthetic.make_c2(n=n, D=DIM, seed=5)
+    grid = choose_grid(world)
+    solver = DistributedGp(grid=grid, nb=nb, device=local)
+    times, fit = [], None
+    for _ in range(reps):
+        fit = solver.fit(X, y, theta)
+        times.append(_max_over_ranks(dist, [fit.seconds])[0])
+    res = solver.residual(y, fit.alphaVec)
+    best = min(times)
+    rec = {"workload": f"C5: one GP, n={n}, D={DIM}, K build + block-cyclic Cholesky (nb={nb}) + alpha solves + log-likelihood",
+           "scaling": "strong", "grid": f"{grid[0]}x{grid[1]}", "seconds": best, "seconds_all": times,
+           "potrf_tflops_total": float(n) ** 3 / 3 / best * 1e-12, "potrf_tflops_per_gpu": float(n) ** 3 / 3 / best * 1e-12 / world,
+           "residual_Kalpha_minus_y_over_y": res, "ll": fit.logLikelihood,
+           "bytes_broadcast_received_per_rank": int(getattr(solver, "bcast_bytes", 0) // max(reps, 1)),
+           "collectives": "none (1 GPU)" if world == 1 else "NCCL broadcast of L_kk^-1 and the panel pieces per step, one nb-vector "
+                          "all-reduce per back-solve step, two scalar all-reduces",
+           "timing": "CUDA events around build + factor + solves on each rank, max over ranks, best of %d" % reps}
+    del solver
+    torch.cuda.empty_cache()
+    return rec
+
+
+def nccl_parity(dist, rank, world, local, g0, n=5000, nb=256):
+    """N >= 2 only: the NCCL data plane against the same solver on a 1 x 1 grid (rank 0 alone), in this run, because the
+    2-GPU pytest cannot run on a 1-GPU test box.  ll to 1e-11, alpha to 1e-9, K alpha = y to 1e-10."""
+    import numpy as np
+    import torch
+    from gp_algos_b200 import synthetic
+    from gp_algos_b200.distributed import DistributedGp, choose_grid
+    X, y, theta = synthetic.make_c2(n=n, D=DIM, seed=5)
+    grid = choose_grid(world)
+    solver = DistributedGp(grid=grid, nb=nb, device=local)
+    fit = solver.fit(X, y, theta)
+    res = solver.residual(y, fit.alphaVec)
+    rec = {"n": n, "nb": nb, "grid": f"{grid[0]}x{grid[1]}", "residual_Kalpha_minus_y_over_y": res}
+    ok = torch.zeros(1, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        single = DistributedGp(grid=(1, 1), nb=nb, device=local, group=g0)
+        fit1 = single.fit(X, y, theta)
+        rec["ll_rel_diff_vs_1x1"] = abs(fit.logLikelihood - fit1.logLikelihood) / abs(fit1.logLikelihood)
+        rec["alpha_max_rel_diff_vs_1x1"] = float(np.abs(fit.alphaVec - fit1.alphaVec).max() / np.abs(fit1.alphaVec).max())
+        rec["passed"] = bool(rec["ll_rel_diff_vs_1x1"] <= 1e-11 and rec["alpha_max_rel_diff_vs_1x1"] <= 1e-9 and res < 1e-10)
+        ok[0] = 1.0 if rec["passed"] else 0.0
+    dist.broadcast(ok, src=0)
+    rec["passed"] = bool(ok.item() == 1.0)
+    return rec
+
+
+def run_sharded(h, dist, rank, world, local):
+    rec = {}
+    g0 = dist.new_group(ranks=[0]) if dist is not None else None     # rank 0 alone: the in-run single-GPU references
+    for name, fn in (("c4", lambda: bench_c4(h, dist, rank, world)),
+                     ("c5", lambda: bench_c5(dist, rank, world, local)),
+                     ("nccl_parity", (lambda: nccl_parity(dist, rank, world, local, g0)) if world > 1 else None)):
+        if fn is None:
+            continue
+        try:
+            rec[name] = fn()
+        except Exception as e:  # keep the headline line; a failed sharded leg is reported, not hidden
+            rec[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+    return rec
+
+
+def syrk_traffic(nn, kk):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch of the SYRK kernel at this shape, taken from
+    the committed `ncu --set full` capture summary (profiles/syrk_traffic.json, written by tools/ncu_traffic.py from the
+    .ncu-rep); DRAM traffic cannot be measured outside a profiler, so it is null when no capture of this shape is recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "syrk_traffic.json")) as f:
+            t = json.load(f)
+        if (t.get("n"), t.get("k")) == (nn, kk):
+            return {"traffic": float(t["dram_bytes_per_launch"]), "traffic_source": t.get("source"),
+                    "algorithmic_bytes": 8.0 * (nn * (nn + 128) / 2 * 2 + nn * kk)}
+    except Exception:
+        pass
+    return {"traffic": None}
 
 
 def run_gpk(args):
@@ -259,19 +504,27 @@ def run_gpk(args):
         roofline = {"kernel": "gemm_f64_dmma_kernel<false,false,SmallTile 64x64> as the Cholesky trailing update (SYRK lower, "
                               f"n={nn}, k={kk})", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": ach / peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel and shape from the ncu --set full capture in
-                    # profiles/r01_ncu_summary_v3.txt (608.4 + 60.3 MB; algorithmic 268 MB), bytes per launch
-                    "traffic": 668.71e6 if (nn, kk) == (4096, 4096) else None,
+                    **syrk_traffic(nn, kk),
                     "peak_source": f"cuBLAS Dgemm {n}^3 measured live in this run (MEASURED_PEAKS.json has no FP64 entry; "
                                    "DMMA pipe ceiling 37.1 TFLOP/s, profiles/r01_fp64_microbench.txt)",
                     "eval_flops": float(n) ** 3, "eval_tflops": float(n) ** 3 / (ms / args.steps) * 1e-9,
                     "eval_frac_of_peak": float(n) ** 3 / (ms / args.steps) * 1e-9 / peak}
         del A, B, Co, P, Cm
 
+    cholesky = None
+    if rank == 0:
+        try:
+            cholesky = bench_cholesky(h, dX, n, theta, roofline["peak"])
+        except Exception as e:
+            cholesky = {"error": f"{type(e).__name__}: {e}"[:400]}
+    sharded = None
+    if not args.no_sharded:
+        sharded = run_sharded(h, dist, rank, world, local)
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count()
+            cores = blas_threads_all()
             t_cpu = cpu_eval_time(n)
             t_lit = cpu_literal_time(768)
             cpu = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
@@ -285,7 +538,8 @@ def run_gpk(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(n, world),
             "e2e": {"value": world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": (n * DIM + n) * 8,
                     "d2h_bytes_per_step": (NPARAMS + 1) * 8 + 4},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cholesky": cholesky, "sharded": sharded,
+            "cpu_baseline": cpu,
             "result": {"ll": float(res_dev[0]), "grad_inf_norm": float(np.abs(res_dev[1:]).max())},
         }
         print(json.dumps(out))

@@ -75,6 +75,7 @@ def load():
         lib.gpk_cov_cross_se_ard_dev.argtypes = [vp, vp, ci, _i64, vp, ci, _i64, ci, vp, vp, _i64]
         lib.gpk_cov_deriv_se_ard.argtypes = [vp, ci, vp, ci, ci, _i64, vp, vp, _i64]
         lib.gpk_potrf_lower.argtypes = [vp, vp, ci, _i64, vp, _i64, ci]
+        lib.gpk_potrf_lower_dev.argtypes = [vp, vp, ci, _i64, vp]
         lib.gpk_trsm.argtypes = [vp, ci, ci, vp, ci, _i64, vp, ci, _i64, vp, _i64]
         lib.gpk_trtri.argtypes = [vp, ci, vp, ci, _i64, vp, _i64]
         lib.gpk_syrk_lower_dev.argtypes = [vp, vp, _i64, vp, _i64, ci, ci]

@@ -34,7 +34,9 @@ def _stack_problems(X, B):
     if X.ndim != 3 or X.shape[0] != B:
         raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, "X must be (n, D) or (B, n, D)")
     n, D = X.shape[1], X.shape[2]
-    buf = np.ascontiguousarray(np.transpose(X, (0, 2, 1)))  # (B, D, n) C-order == B column-major n x D blocks
+    # (B, D, n) C-order == B column-major n x D blocks (Breeze DenseMatrix layout); no copy when the caller's stack already
+    # is one, e.g. np.empty((B, D, n)).transpose(0, 2, 1) over pinned memory
+    buf = np.ascontiguousarray(np.transpose(X, (0, 2, 1)))
     return buf, n * D, n, D
 
 

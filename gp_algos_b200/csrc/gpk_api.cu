@@ -100,6 +100,8 @@ int gpk_create(gpk_handle* out, int device, void* stream) {
         if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, greatest) != cudaSuccess) { delete h; return GPK_ECUDA; }
         h->own_stream = true;
     }
+    h->main_stream = h->stream;
+    if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->num_sms <= 0) h->num_sms = 148;
     if (cudaMallocHost((void**)&h->h_pinned, 4096 * sizeof(double)) != cudaSuccess ||
         cudaMalloc((void**)&h->d_info, 4 * sizeof(int)) != cudaSuccess) {
         delete h;
@@ -143,6 +145,7 @@ int gpk_destroy(gpk_handle h) {
     for (int i = 0; i < GPK_NARENA; ++i)
         if (h->arena[i]) cudaFree(h->arena[i]);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->res_pinned) cudaFreeHost(h->res_pinned);
     if (h->d_info) cudaFree(h->d_info);
     for (int i = 0; i < GPK_NEVENTS; ++i)
         if (h->evpool[i]) cudaEventDestroy(h->evpool[i]);
@@ -273,7 +276,7 @@ int gpk_potrf_lower(gpk_handle h, const double* A, int n, int64_t lda, double* L
         GPK_CUDA(h, cudaStreamSynchronize(h->stream));
         if (ns) return gpk_set_error(h, GPK_ENOTSYM, "matrix is not symmetric");
     }
-    rc = gpk_potrf_inv(h, dA, dLi, dT, N, 1, h->d_info, 1);
+    rc = gpk_potrf_factor(h, dA, dLi, dT, N, h->d_info);     // L only: n^3/3 flops (no L^-1, no K^-1)
     if (rc) return rc;
     rc = gpk_store_lower(h, dIn, n, dA, N, n);
     if (rc) return rc;
@@ -307,6 +310,70 @@ int gpk_trtri(gpk_handle h, int is_upper, const double* T, int n, int64_t ldt, d
     return gpk_synchronize(h);
 }
 
+// Blocked substitution on the padded lower-triangular Lw (N x N, ld N) with the inverses of its 128 x 128 diagonal blocks
+// (Di: block k at Di + k*128*128, ld 128).  O(n^2) work per right-hand side, nothing n x n is inverted:
+//   forward  (X = Lw^-1 B):  X1 = solve(L11, B1);  B2 -= L21 X1;    X2 = solve(L22, B2)
+//   backward (X = Lw^-t B):  X2 = solve(L22^t, B2); B1 -= L21^t X2;  X1 = solve(L11^t, B1)
+// with the 128-row base case X_k = Di_k B_k (or Di_k^t B_k).  B is overwritten; X is a second buffer of the same shape.
+// M > 0: B, X are N x M (ld N) and every step is a DMMA GEMM; M == 0: one vector, every step is an HBM-bound mat-vec.
+}  // extern "C"
+namespace {
+int trsm_rec(gpk_handle h, const double* Lw, const double* Di, int N, int backward, double* B, double* X, int M, int r0, int len) {
+    if (len == GPK_TILE) {
+        const double* Dk = Di + (size_t)(r0 / GPK_TILE) * GPK_TILE * GPK_TILE;
+        if (M == 0) return gpk_gemv(h, backward, GPK_TILE, GPK_TILE, 1.0, Dk, GPK_TILE, B + r0, 0.0, X + r0);
+        GemmDesc g = gemm_desc();
+        g.P = B + r0; g.ldp = N; g.p_kcontig = 1;              // P(r,k) = B_k(k, r)
+        g.Q = Dk; g.ldq = GPK_TILE;
+        g.D = X + r0; g.ldd = N; g.R = M; g.S = GPK_TILE; g.K = GPK_TILE;
+        if (!backward) { g.q_kcontig = 0; g.ke_s = 1; }        // Q(s,k) = Di_k(s,k), zero for k > s
+        else           { g.q_kcontig = 1; g.kb_s = 1; }        // Q(s,k) = Di_k(k,s), zero for k < s
+        return gpk_gemm(h, g);
+    }
+    const int n1 = (len / GPK_TILE / 2) * GPK_TILE, n2 = len - n1;
+    const double* L21 = Lw + (r0 + n1) + (int64_t)r0 * N;
+    int rc;
+    if (!backward) {
+        rc = trsm_rec(h, Lw, Di, N, 0, B, X, M, r0, n1);
+        if (rc) return rc;
+        if (M == 0) rc = gpk_gemv(h, 0, n2, n1, -1.0, L21, N, X + r0, 1.0, B + r0 + n1);
+        else {
+            GemmDesc g = gemm_desc();
+            g.P = X + r0; g.ldp = N; g.p_kcontig = 1;          // P(r,k) = X1(k, r)
+            g.Q = L21; g.ldq = N; g.q_kcontig = 0;             // Q(s,k) = L21(s, k)
+            g.D = B + r0 + n1; g.ldd = N; g.Cin = g.D; g.ldc = N;
+            g.R = M; g.S = n2; g.K = n1; g.alpha = -1.0; g.beta = 1.0;
+            rc = gpk_gemm(h, g);
+        }
+        if (rc) return rc;
+        return trsm_rec(h, Lw, Di, N, 0, B, X, M, r0 + n1, n2);
+    }
+    rc = trsm_rec(h, Lw, Di, N, 1, B, X, M, r0 + n1, n2);
+    if (rc) return rc;
+    if (M == 0) rc = gpk_gemv(h, 1, n2, n1, -1.0, L21, N, X + r0 + n1, 1.0, B + r0);
+    else {
+        GemmDesc g = gemm_desc();
+        g.P = X + r0 + n1; g.ldp = N; g.p_kcontig = 1;         // P(r,k) = X2(k, r)
+        g.Q = L21; g.ldq = N; g.q_kcontig = 1;                 // Q(s,k) = L21(k, s)
+        g.D = B + r0; g.ldd = N; g.Cin = g.D; g.ldc = N;
+        g.R = M; g.S = n1; g.K = n2; g.alpha = -1.0; g.beta = 1.0;
+        rc = gpk_gemm(h, g);
+    }
+    if (rc) return rc;
+    return trsm_rec(h, Lw, Di, N, 1, B, X, M, r0, n1);
+}
+}  // namespace
+
+// Lw: padded lower factor on the device.  Inverts its diagonal 128-blocks into Di (one launch) and substitutes.
+int gpk_trsm_padded(gpk_handle h, const double* Lw, double* Di, int N, int backward, double* B, double* X, int M) {
+    int rc = gpk_base_potrf_trtri(h, const_cast<double*>(Lw), N, Di, GPK_TILE, h->d_info + 2, 0, 1, N / GPK_TILE,
+                                  (int64_t)GPK_TILE * (N + 1), (int64_t)GPK_TILE * GPK_TILE, 0, GPK_TILE);
+    if (rc) return rc;
+    return trsm_rec(h, Lw, Di, N, backward, B, X, M, 0, N);
+}
+
+extern "C" {
+
 int gpk_trsm(gpk_handle h, int upper, int transposed, const double* T, int n, int64_t ldt, const double* B, int nrhs,
              int64_t ldb, double* Xout, int64_t ldx) {
     if (!h || n < 0 || nrhs < 0 || ldt < n || ldb < n || ldx < n) return gpk_set_error(h, GPK_EINVAL, "gpk_trsm: bad dimensions");
@@ -314,34 +381,56 @@ int gpk_trsm(gpk_handle h, int upper, int transposed, const double* T, int n, in
     GPK_CUDA(h, cudaSetDevice(h->device));
     // The stored matrix is lower triangular iff (upper XOR transposed) == 0.
     const int stored_upper = (upper != 0) != (transposed != 0);
-    const int N = gpk_pad(n), M = gpk_pad(nrhs);
+    // a handful of right-hand sides go column by column through the mat-vec path (no padding to a 128-column GEMM operand)
+    const bool vec = nrhs <= 4;
+    const int N = gpk_pad(n), M = vec ? nrhs : gpk_pad(nrhs);
     ARENA_OR_FAIL(dIn, double*, h, ARENA_IO, (size_t)n * n * sizeof(double));
     ARENA_OR_FAIL(dA, double*, h, ARENA_A, (size_t)N * N * sizeof(double));
-    ARENA_OR_FAIL(dLi, double*, h, ARENA_B, (size_t)N * N * sizeof(double));
-    ARENA_OR_FAIL(dT, double*, h, ARENA_T, gpk_chol_scratch_doubles(N) * sizeof(double));
+    ARENA_OR_FAIL(dDi, double*, h, ARENA_T, (size_t)N * GPK_TILE * sizeof(double));
     ARENA_OR_FAIL(dB, double*, h, ARENA_IO2, (size_t)2 * N * M * sizeof(double));
     double* dX = dB + (size_t)N * M;
     int rc = gpk_upload_matrix(h, dIn, T, n, n, ldt);
     if (rc) return rc;
     rc = gpk_load_tri_padded(h, dA, N, dIn, n, n, stored_upper);   // dA = lower-triangular Lw (= stored or stored^t)
     if (rc) return rc;
-    rc = gpk_trtri_lower(h, dA, dLi, dT, N);                        // dLi = Lw^-1
-    if (rc) return rc;
-    GPK_CUDA(h, cudaMemsetAsync(dB, 0, (size_t)N * M * sizeof(double), h->stream));
+    GPK_CUDA(h, cudaMemsetAsync(dB, 0, (size_t)2 * N * M * sizeof(double), h->stream));
     GPK_CUDA(h, cudaMemcpy2DAsync(dB, (size_t)N * sizeof(double), B, (size_t)ldb * sizeof(double), (size_t)n * sizeof(double),
                                   (size_t)nrhs, cudaMemcpyHostToDevice, h->stream));
     // effective operand E: lower (forwardSolve) -> E = Lw, X = Lw^-1 B;  upper (backSolve) -> E = Lw^t, X = Lw^-t B
-    GemmDesc g = gemm_desc();
-    g.P = dB; g.ldp = N; g.p_kcontig = 1;            // P(r,k) = B(k,r)
-    g.Q = dLi; g.ldq = N;
-    g.D = dX; g.ldd = N; g.R = M; g.S = N; g.K = N;
-    if (!upper) { g.q_kcontig = 0; g.ke_s = 1; }     // Q(s,k) = Lw^-1(s,k), zero for k > s
-    else        { g.q_kcontig = 1; g.kb_s = 1; }     // Q(s,k) = Lw^-1(k,s), zero for k < s
-    rc = gpk_gemm(h, g);
+    if (vec) {
+        rc = gpk_base_potrf_trtri(h, dA, N, dDi, GPK_TILE, h->d_info + 2, 0, 1, N / GPK_TILE, (int64_t)GPK_TILE * (N + 1),
+                                  (int64_t)GPK_TILE * GPK_TILE, 0, GPK_TILE);
+        for (int c = 0; c < nrhs && !rc; ++c)
+            rc = trsm_rec(h, dA, dDi, N, upper ? 1 : 0, dB + (size_t)c * N, dX + (size_t)c * N, 0, 0, N);
+    } else {
+        rc = gpk_trsm_padded(h, dA, dDi, N, upper ? 1 : 0, dB, dX, M);
+    }
     if (rc) return rc;
     GPK_CUDA(h, cudaMemcpy2DAsync(Xout, (size_t)ldx * sizeof(double), dX, (size_t)N * sizeof(double), (size_t)n * sizeof(double),
                                   (size_t)nrhs, cudaMemcpyDeviceToHost, h->stream));
     return gpk_synchronize(h);
+}
+
+// Cholesky of a device-resident matrix, in place: on exit the lower triangle of dA holds L and the strict upper triangle is
+// zero (Breeze `cholesky` semantics, GpPredictor.scala:120).  Asynchronous on the handle's stream; info_dev (device int, may
+// be null -> gpk_last_info after gpk_synchronize is NOT updated) receives 0 or the failing leading minor.
+int gpk_potrf_lower_dev(gpk_handle h, double* dA, int n, int64_t lda, int* info_dev) {
+    if (!h || !dA || n <= 0 || lda < n) return gpk_set_error(h, GPK_EINVAL, "gpk_potrf_lower_dev: bad dimensions");
+    const int N = gpk_pad(n);
+    ARENA_OR_FAIL(dLi, double*, h, ARENA_B, (size_t)N * N * sizeof(double));
+    ARENA_OR_FAIL(dT, double*, h, ARENA_T, gpk_chol_scratch_doubles(N) * sizeof(double));
+    int* info = info_dev ? info_dev : h->d_info;
+    if (N == n && lda == n && !((uintptr_t)dA & 15)) {
+        int rc = gpk_potrf_factor(h, dA, dLi, dT, N, info);
+        if (rc) return rc;
+        return gpk_store_lower(h, dA, n, dA, N, n);     // zero the strict upper triangle (element-wise, in place)
+    }
+    ARENA_OR_FAIL(dW, double*, h, ARENA_A, (size_t)N * N * sizeof(double));
+    int rc = gpk_load_sym_padded(h, dW, N, dA, n, lda, nullptr);
+    if (rc) return rc;
+    rc = gpk_potrf_factor(h, dW, dLi, dT, N, info);
+    if (rc) return rc;
+    return gpk_store_lower(h, dA, lda, dW, N, n);
 }
 
 int gpk_syrk_lower_dev(gpk_handle h, const double* dP, int64_t ldp, double* dC, int64_t ldc, int n, int k) {

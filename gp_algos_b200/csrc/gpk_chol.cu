@@ -60,10 +60,23 @@ int pipe_min() {     // smallest padded N that takes the pipelined driver (0 dis
     return v;
 }
 
+int potrf_nb();
+
 int batch_group_min() {   // smallest batch that is split into GPK_NGROUP concurrent groups (0 or less: never)
     static int v = -1;
     if (v < 0) { const char* e = getenv("GPK_GROUP_MIN"); v = e ? atoi(e) : 8; if (v <= 0) v = 1 << 30; }
     return v;
+}
+
+// Number of concurrent batch groups: 2 from 8 problems on, 4 from 32 on (GPK_NGROUPS overrides the count, GPK_GROUP_MIN the
+// threshold).  Measured on B200, 64 problems of n = 1024: see profiles/r02_c4_groups.log.
+int batch_groups(int batch) {
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("GPK_NGROUPS"); forced = e ? atoi(e) : -1; if (forced > GPK_NGROUP) forced = GPK_NGROUP; }
+    if (batch < batch_group_min()) return 1;
+    int g = forced > 0 ? forced : (batch >= 32 ? 4 : 2);
+    while (g > 1 && batch / g < 4) g /= 2;
+    return g;
 }
 
 void set_batch(GemmDesc& g, const Ctx& c, int64_t sP, int64_t sQ, int64_t sD, int64_t sC) {
@@ -179,7 +192,9 @@ static size_t rec_scratch_doubles(int N) {
 size_t gpk_chol_scratch_doubles(int N) {
     const size_t rec = rec_scratch_doubles(N);
     const size_t pipe = rec_scratch_doubles(pipe_nb()) + (size_t)pipe_nb() * N;   // diagonal-block scratch + one row panel
-    return rec > pipe ? rec : pipe;
+    const size_t fact = rec_scratch_doubles(potrf_nb());
+    const size_t m = rec > pipe ? rec : pipe;
+    return m > fact ? m : fact;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -235,9 +250,17 @@ int col_update(gpk_handle h, double* A, const double* Li, int N, int bk, int sk,
 
 }  // namespace
 
+namespace {
+int potrf_nb() {     // block-column width of the factor-only driver (gpk_potrf_factor)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GPK_POTRF_NB"); v = e ? atoi(e) : 512; if (v < NB || v % NB) v = 512; }
+    return v;
+}
+}  // namespace
+
 int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev,
-                            cudaEvent_t* kinv_done) {
-    const int nbk = pipe_nb();
+                            cudaEvent_t* kinv_done, int factor_only) {
+    const int nbk = factor_only ? potrf_nb() : pipe_nb();
     const int nt = (N + nbk - 1) / nbk;
     auto bs = [&](int k) { return k * nbk < N ? k * nbk : N; };
     GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
@@ -248,7 +271,7 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     cudaEvent_t ev = next_event(h);
     GPK_CUDA(h, cudaEventRecord(ev, M));            // K is built (and earlier users of the buffers are done) before S/S2 start
     GPK_CUDA(h, cudaStreamWaitEvent(S, ev, 0));
-    GPK_CUDA(h, cudaStreamWaitEvent(S2, ev, 0));
+    if (!factor_only) GPK_CUDA(h, cudaStreamWaitEvent(S2, ev, 0));
     if (Kinv) GPK_CUDA(h, cudaStreamWaitEvent(S3, ev, 0));   // (a stream that is forked must also be joined: graph capture insists)
     cudaEvent_t evGcol_prev = nullptr;              // S finished block column k+1 of trailing update k-1
     cudaEvent_t evLi = nullptr;                     // S2 finished the last row of L^-1
@@ -299,6 +322,7 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
                 tr.mark(S, "S:U", k);
             }
         }
+        if (factor_only) continue;     // only L (and the diagonal-block inverses the panels were solved with) is wanted
         GPK_CUDA(h, cudaStreamWaitEvent(S2, evF, 0));
         StreamSwap sw(h, S2);
         const double* Likk = Li + bk + (int64_t)bk * N;
@@ -353,6 +377,7 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     cudaEvent_t e1 = next_event(h), e2 = next_event(h);
     GPK_CUDA(h, cudaEventRecord(e1, S));
     GPK_CUDA(h, cudaStreamWaitEvent(M, e1, 0));
+    if (factor_only) return GPK_OK;
     GPK_CUDA(h, cudaEventRecord(e2, Kinv ? S3 : S2));   // no K^-1 requested: S3 was never forked, join the row chain
     if (kinv_done && Kinv && evLi) {
         GPK_CUDA(h, cudaStreamWaitEvent(M, evLi, 0));
@@ -364,13 +389,21 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     return GPK_OK;
 }
 
+// Factor only (LAPACK dpotrf 'L': GpPredictor.scala:120, EpParameterEstimator.scala:58 when the caller wants nothing but L): the
+// look-ahead driver without the inverse rows and the K^-1 accumulation -- n^3/3 flops instead of n^3.  Only the diagonal
+// blocks are inverted (the panels are solved as GEMMs with them).  Li is still an N x N staging area.
+int gpk_potrf_factor(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev) {
+    if (N >= 2 * potrf_nb()) return gpk_potrf_inv_pipelined(h, A, Li, nullptr, T, N, 1, info_dev, nullptr, 1);
+    return gpk_potrf_inv(h, A, Li, T, N, 1, info_dev, 1);
+}
+
 bool gpk_use_pipelined(int N, int batch) { return batch == 1 && pipe_min() > 0 && N >= pipe_min() && N >= 2 * pipe_nb(); }
 
 int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int* info_dev, int batch) {
     if (gpk_use_pipelined(N, batch)) return gpk_potrf_inv_pipelined(h, A, Li, nullptr, T, N, keep_L, info_dev, nullptr);
     GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int) * (size_t)batch, h->stream));
     const int64_t sM = (int64_t)N * N, sT = (int64_t)gpk_chol_scratch_doubles(N);
-    const int groups = (batch >= batch_group_min()) ? GPK_NGROUP : 1;
+    const int groups = batch_groups(batch);
     if (groups == 1) {
         Ctx c{h, N, N, keep_L, info_dev, batch, sM, sT, 0};
         return potrf_inv_rec(c, A, Li, T, N, 0, 0);

@@ -330,28 +330,35 @@ int gpk_gp_nll_grad_batched(gpk_handle h, int B, const double* X, int n, int D, 
     double* dout = dy + (size_t)B * n;
     int* dinfo = (int*)(dout + B * so);
     int rc = GPK_OK;
-    for (int b = 0; b < nx && !rc; ++b) rc = gpk_upload_matrix(h, dX + (size_t)b * n * D, X + b * strideX, n, D, ldx);
-    if (rc) return rc;
+    if (ldx == n && (nx == 1 || strideX == (int64_t)n * D)) {
+        // the stack is one contiguous block (Breeze matrices laid out back to back): a single copy
+        GPK_CUDA(h, cudaMemcpyAsync(dX, X, (size_t)nx * n * D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int b = 0; b < nx && !rc; ++b) rc = gpk_upload_matrix(h, dX + (size_t)b * n * D, X + b * strideX, n, D, ldx);
+        if (rc) return rc;
+    }
     GPK_CUDA(h, cudaMemcpyAsync(dy, y, (size_t)B * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     rc = gpk_gp_nll_grad_batched_dev(h, B, dX, n, D, n, strideX ? (int64_t)n * D : 0, dy, thetas, has_s, s, nparams, dout, dinfo);
     if (rc) return rc;
-    double* hout = (double*)malloc(B * so * sizeof(double));
-    int* hinfo = (int*)malloc((size_t)B * sizeof(int));
-    if (!hout || !hinfo) { free(hout); free(hinfo); return gpk_set_error(h, GPK_ENOMEM, "host allocation failed"); }
-    cudaError_t e1 = cudaMemcpyAsync(hout, dout, B * so * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    cudaError_t e2 = cudaMemcpyAsync(hinfo, dinfo, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-    cudaError_t e3 = cudaStreamSynchronize(h->stream);
-    int bad = 0;
-    if (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) {
-        for (int b = 0; b < B; ++b) {
-            ll[b] = hout[b * so];
-            for (int p = 0; p < nparams; ++p) grad[(size_t)b * nparams + p] = hout[b * so + 1 + p];
-            if (info) info[b] = hinfo[b];
-            if (hinfo[b] && !bad) { bad = 1; h->last_info = hinfo[b]; }
-        }
+    // results come back through the handle's pinned staging buffer (grown on demand, never per call)
+    const size_t res_bytes = B * so * sizeof(double) + (size_t)B * sizeof(int);
+    if (h->res_pinned_bytes < res_bytes) {
+        if (h->res_pinned) cudaFreeHost(h->res_pinned);
+        h->res_pinned = nullptr; h->res_pinned_bytes = 0;
+        if (cudaMallocHost(&h->res_pinned, res_bytes) != cudaSuccess) { cudaGetLastError(); return gpk_set_error(h, GPK_ENOMEM, "pinned host allocation failed"); }
+        h->res_pinned_bytes = res_bytes;
     }
-    free(hout); free(hinfo);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return gpk_set_error(h, GPK_ECUDA, "result download failed");
+    double* hout = (double*)h->res_pinned;
+    int* hinfo = (int*)(hout + B * so);
+    GPK_CUDA(h, cudaMemcpyAsync(hout, dout, res_bytes, cudaMemcpyDeviceToHost, h->stream));   // dinfo follows dout on the device too
+    GPK_CUDA(h, cudaStreamSynchronize(h->stream));
+    int bad = 0;
+    for (int b = 0; b < B; ++b) {
+        ll[b] = hout[b * so];
+        for (int p = 0; p < nparams; ++p) grad[(size_t)b * nparams + p] = hout[b * so + 1 + p];
+        if (info) info[b] = hinfo[b];
+        if (hinfo[b] && !bad) { bad = 1; h->last_info = hinfo[b]; }
+    }
     if (bad) return gpk_set_error(h, GPK_ENOTPD, "at least one problem of the batch is not positive definite (see info[])");
     return GPK_OK;
 }

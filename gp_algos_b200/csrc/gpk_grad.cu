@@ -239,7 +239,10 @@ int gpk_grad_trace(gpk_handle h, const double* Kinv, int N, const double* dX, in
     a.strideX = strideX; a.pp = pp_dev;
     const size_t smem = (size_t)2 * D * GT * sizeof(double);
     if (smem > 48 * 1024 && !(h->func_cfg & (1u << 9))) {
-        GPK_CUDA(h, cudaFuncSetAttribute(grad_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // opt in once for the LARGEST request any later call can make (D = GPK_MAX_D): a handle that sees D = 50 first and
+        // D = 64 afterwards must not be left with the smaller limit
+        GPK_CUDA(h, cudaFuncSetAttribute(grad_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)2 * GPK_MAX_D * GT * sizeof(double))));
         h->func_cfg |= (1u << 9);
     }
     if (pp.cp.kind == GPK_KERNEL_CO2) grad_trace_co2_kernel<<<dim3(nblocks, batch), 256, 0, h->stream>>>(a);

@@ -9,13 +9,15 @@
 
 #define GPK_TILE 128
 #define GPK_NPIPE 3
-#define GPK_NSIDE 8      // side streams (one per recursion depth, cyclic; batch group g starts at 4*g)
-#define GPK_NGROUP 2     // batch groups of the batched factorisation: group 0 on the handle's stream, the others on grp[]
+#define GPK_NSIDE 16     // side streams (one per recursion depth, cyclic; batch group g starts at 4*g)
+#define GPK_NGROUP 4     // batch groups of the batched factorisation: group 0 on the handle's stream, the others on grp[]
 #define GPK_NEVENTS 256  // fork/join event pool (cyclic)  // every internal matrix dimension / leading dimension is a multiple of this
 
 struct gpk_handle_s {
     int device;
-    cudaStream_t stream;
+    cudaStream_t stream;       // the stream launches go to (temporarily swapped to a side / pipe stream by the drivers)
+    cudaStream_t main_stream;  // the handle's own stream: never swapped
+    int num_sms;
     bool own_stream;
     cudaStream_t side[GPK_NSIDE];
     cudaStream_t grp[GPK_NGROUP - 1];   // same priority as the main stream
@@ -23,9 +25,11 @@ struct gpk_handle_s {
     cudaEvent_t evpool[GPK_NEVENTS];
     unsigned ev_next;
     // grow-only device arenas (A: factor / K^-1, B: L^-1, T: GEMM scratch, misc: small vectors)
-    void* arena[12];
-    size_t arena_bytes[12];
+    void* arena[16];
+    size_t arena_bytes[16];
     double* h_pinned;  // 4096 doubles of pinned host scratch
+    void* res_pinned;          // grow-only pinned staging for the results of batched calls
+    size_t res_pinned_bytes;
     int* d_info;       // device int: first failing minor of the last factorisation
     int last_info;
     int64_t launches;
@@ -56,7 +60,7 @@ int gpk_graph_run(gpk_handle h, int slot, const GraphKey& key, int eager_calls, 
     return gpk_graph_run_impl(h, slot, key, eager_calls, [](void* c) { return (*static_cast<F*>(c))(); }, &body, what);
 }
 
-enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7, ARENA_PP = 8, ARENA_INFO = 9, ARENA_GEMV = 10, ARENA_KINV = 11, GPK_NARENA = 12 };
+enum { ARENA_A = 0, ARENA_B = 1, ARENA_T = 2, ARENA_MISC = 3, ARENA_X = 4, ARENA_IO = 5, ARENA_IO2 = 6, ARENA_IO3 = 7, ARENA_PP = 8, ARENA_INFO = 9, ARENA_GEMV = 10, ARENA_KINV = 11, ARENA_SK = 12, GPK_NARENA = 13 };
 
 int gpk_set_error(gpk_handle h, int status, const char* fmt, ...);
 // returns device pointer to at least `bytes` bytes in arena `which` (contents undefined after growth)
@@ -216,7 +220,13 @@ bool gpk_use_pipelined(int N, int batch);
 // kinv_done != nullptr: returns without waiting for the K^-1 accumulation; the caller must cudaStreamWaitEvent(*kinv_done)
 // (when non-null) on its stream before reading Kinv.
 int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev,
-                            cudaEvent_t* kinv_done = nullptr);
+                            cudaEvent_t* kinv_done = nullptr, int factor_only = 0);
+// L only (plus the inverses of the diagonal blocks, left in Li's diagonal blocks): n^3/3 flops.  Li: N x N staging.
+int gpk_potrf_factor(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev);
+// X = Lw^-1 B (backward == 0) or Lw^-t B (backward != 0) by blocked substitution on the padded lower factor Lw (N x N, ld N).
+// Di: N x 128 scratch for the inverses of the diagonal blocks.  M > 0: B, X are N x M (ld N, M a multiple of 128);
+// M == 0: one vector.  B is overwritten.
+int gpk_trsm_padded(gpk_handle h, const double* Lw, double* Di, int N, int backward, double* B, double* X, int M);
 // L^-1 for a given lower-triangular L (N x N padded, ld N)
 int gpk_trtri_lower(gpk_handle h, const double* L, double* Li, double* T, int N);
 // Kinv (lower triangle incl. diagonal tiles in full) = Li^t Li

@@ -232,6 +232,7 @@ class DistributedGp:
         self.ops = ops
         self.A = None
         self.launch_gemm = 0
+        self.bcast_bytes = 0          # bytes this rank sent or received through broadcasts (bench.py reports it)
 
     # -- communication (no-ops on a 1 x 1 grid) -----------------------------------------------------------------
     def _global_rank(self, r: int) -> int:
@@ -240,6 +241,7 @@ class DistributedGp:
     def _bcast(self, t, src: int):
         if self.world == 1:
             return None
+        self.bcast_bytes += t.numel() * t.element_size()
         return self.dist.broadcast(t, src=self._global_rank(src), group=self.group, async_op=True)
 
     def _allreduce(self, t, op=None):

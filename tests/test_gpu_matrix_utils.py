@@ -150,3 +150,51 @@ def test_inv_triangular(n):
     Ui = MU.invTriangular(np.ascontiguousarray(L.T), isUpper=True)
     assert np.all(np.tril(Ui, -1) == 0.0)
     assert np.allclose(Ui, ref.T, rtol=1e-9, atol=1e-12)
+
+
+# ---- device-resident factor-only Cholesky (gpk_potrf_lower_dev) and large solves ---------------------------
+@pytest.mark.parametrize("n,lda", [(1024, 1024), (1000, 1100), (2304, 2304), (130, 130)])
+def test_potrf_lower_dev_in_place(n, lda):
+    import scipy.linalg as sla
+    import torch
+    from gp_algos_b200 import _lib
+    X, y, th = orc.make_c2(n=n, D=8, seed=n + 3)
+    K = orc.fast_build_kernel_matrix(X, th)
+    buf = np.full((n, lda), 7.0)                        # column-major n x n block inside an lda-strided buffer: buf[c, r]
+    buf[:, :n] = K.T
+    d = torch.from_numpy(buf.reshape(-1).copy()).cuda()
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    h = _lib.default_handle()
+    h.check(h.lib.gpk_potrf_lower_dev(h.h, d.data_ptr(), n, lda, info.data_ptr()))
+    h.synchronize()
+    assert int(info.item()) == 0
+    out = d.cpu().numpy().reshape(n, lda)
+    L = out[:, :n].T
+    assert np.all(np.triu(L, 1) == 0.0)
+    assert np.all(out[:, n:] == 7.0)                     # nothing outside the n x n block is touched
+    Lo = sla.cholesky(K, lower=True)
+    assert np.linalg.norm(L @ L.T - K) <= 8 * n * np.finfo(float).eps * np.linalg.norm(K)
+    assert np.linalg.norm(L - Lo) <= 1e-9 * max(np.linalg.cond(K) / 1e5, 1.0) * np.linalg.norm(Lo)
+    assert np.array_equal(L, MU.cholesky(K))             # host and device entry points run the same kernels
+    # not positive definite: the failing leading minor arrives in *info_dev
+    Kb = K.copy(); Kb[n // 2, n // 2] = -1.0
+    buf[:, :n] = Kb.T
+    d = torch.from_numpy(buf.reshape(-1).copy()).cuda()
+    h.check(h.lib.gpk_potrf_lower_dev(h.h, d.data_ptr(), n, lda, info.data_ptr()))
+    h.synchronize()
+    assert int(info.item()) == n // 2 + 1
+
+
+@pytest.mark.parametrize("n,m", [(2500, 1), (2500, 2), (1300, 129)])
+def test_triangular_solves_blocked_substitution_large(n, m):
+    """The blocked O(n^2)-per-right-hand-side substitution at sizes with many diagonal blocks, vector and matrix paths."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(n + m)
+    X, y, th = orc.make_c2(n=n, D=8, seed=n + 11)
+    L = sla.cholesky(orc.fast_build_kernel_matrix(X, th), lower=True)
+    B = rng.standard_normal((n, m)) if m > 1 else rng.standard_normal(n)
+    for got, want in ((MU.forwardSolve(L, B), sla.solve_triangular(L, B, lower=True)),
+                      (MU.backSolve(L, B, transposed=True), sla.solve_triangular(L, B, lower=True, trans="T")),
+                      (MU.backSolve(np.ascontiguousarray(L.T), B), sla.solve_triangular(L, B, lower=True, trans="T"))):
+        assert got.shape == want.shape
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())

@@ -5,7 +5,8 @@ import torch
 from gp_algos_b200 import _lib
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
 h = _lib.Handle(0, ts.cuda_stream)
-n = k = 4096
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+k = int(sys.argv[2]) if len(sys.argv) > 2 else n
 P = torch.randn(k, n, dtype=torch.float64, device="cuda")
 Cm = torch.zeros(n, n, dtype=torch.float64, device="cuda")
 for _ in range(3):
@@ -17,4 +18,4 @@ for _ in range(3):
     h.check(h.lib.gpk_syrk_lower_dev(h.h, P.data_ptr(), n, Cm.data_ptr(), n, n, k))
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
-print(f"syrk n={n} k={k}: {ms:.3f} ms  {n*n*k/ms*1e-9:.2f} TFLOP/s")
+print(f"syrk n={n} k={k} GPK_STREAMK={os.environ.get('GPK_STREAMK', '1')}: {ms:.3f} ms  {n*n*k/ms*1e-9:.2f} TFLOP/s")
