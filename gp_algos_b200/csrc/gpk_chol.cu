@@ -68,13 +68,14 @@ int batch_group_min() {   // smallest batch that is split into GPK_NGROUP concur
     return v;
 }
 
-// Number of concurrent batch groups: 2 from 8 problems on, 4 from 32 on (GPK_NGROUPS overrides the count, GPK_GROUP_MIN the
-// threshold).  Measured on B200, 64 problems of n = 1024: see profiles/r02_c4_groups.log.
+// Number of concurrent batch groups: 2 from 8 problems on (GPK_NGROUPS overrides the count up to 4, GPK_GROUP_MIN the
+// threshold).  Measured on B200 (profiles/r02_c4_groups.log), n = 1024: 64 problems 3.53 / 3.42 / 3.74 ms and 512 problems
+// 24.33 / 23.94 / 24.02 ms with 1 / 2 / 4 groups.
 int batch_groups(int batch) {
     static int forced = -2;
     if (forced == -2) { const char* e = getenv("GPK_NGROUPS"); forced = e ? atoi(e) : -1; if (forced > GPK_NGROUP) forced = GPK_NGROUP; }
     if (batch < batch_group_min()) return 1;
-    int g = forced > 0 ? forced : (batch >= 32 ? 4 : 2);
+    int g = forced > 0 ? forced : 2;
     while (g > 1 && batch / g < 4) g /= 2;
     return g;
 }

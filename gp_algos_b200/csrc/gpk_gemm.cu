@@ -334,10 +334,13 @@ int dispatch(gpk_handle h, const GemmDesc& g, int cfg_id) {
     return g.q_kcontig ? launch<false, true, Cfg>(h, g, cfg_id) : launch<false, false, Cfg>(h, g, cfg_id);
 }
 
-int stream_k_mode() {   // GPK_STREAMK=0 disables the stream-K path
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("GPK_STREAMK"); v = e ? atoi(e) : 1; }
-    return v;
+// GPK_STREAMK=1 enables the stream-K path.  OFF by default -- measured on B200 (profiles/r02_streamk.log): the isolated SYRK
+// n = k = 4096 gains 0.8 % (2.113 -> 2.097 ms), launches with k = 512 lose 11 % (1.016 -> 1.143 ms), and the whole evaluation
+// at n = 8192 loses 10 % (17.40 -> 19.14 ms): persistent CTAs hold every SM slot for the whole launch, so the look-ahead
+// driver's high-priority spine kernels can no longer slip in between the bulk update's short CTAs.
+int stream_k_mode() {   // read at every launch (a getenv, ~50 ns) so that a test can switch it inside one process
+    const char* e = getenv("GPK_STREAMK");
+    return e ? atoi(e) : 0;
 }
 
 // which workspace slot a stream owns: the handle's stream and the three bulk streams of the look-ahead driver; -1 otherwise

@@ -1,10 +1,19 @@
 """GPU: the stream-K path of the DMMA GEMM (csrc/gpk_gemm.cu) against a plain FP64 torch product of the same operands.
-Launches of at least one full wave of 64 x 64 tiles whose tail wave would be partly empty take this path
-(GPK_STREAMK=0 disables it); everything smaller keeps the one-tile-per-CTA kernel."""
+With GPK_STREAMK=1 (the path is opt-in: measured slower inside the look-ahead driver), launches of at least one full wave of
+64 x 64 tiles whose tail wave would be partly empty take it; everything smaller keeps the one-tile-per-CTA kernel."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _enable_stream_k():
+    os.environ["GPK_STREAMK"] = "1"           # read by libgpk at every GEMM launch
+    yield
+    os.environ.pop("GPK_STREAMK", None)
 
 
 def _handle():
