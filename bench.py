@@ -300,7 +300,7 @@ def bench_c4(h, dist, rank, world, reps=5):
     return rec
 
 
-def bench_c5(dist, rank, world, local, n=65536, nb=1024, reps=2):
+def bench_c5(dist, rank, world, local, cpu_group=None, n=65536, nb=1024, reps=2):
     """One GP of n = 65536, D = 8 (seed 5): K build + 2-D block-cyclic FP64 Cholesky + both solves + log-likelihood
     (GpPredictor.scala:104-124,144-149) through DistributedGp.fit.  Strong scaling.  CUDA events per rank, max over ranks."""
     import numpy as np
@@ -324,6 +324,30 @@ def bench_c5(dist, rank, world, local, n=65536, nb=1024, reps=2):
            "collectives": "none (1 GPU)" if world == 1 else "NCCL broadcast of L_kk^-1 and the panel pieces per step, one nb-vector "
                           "all-reduce per back-solve step, two scalar all-reduces",
            "timing": "CUDA events around build + factor + solves on each rank, max over ranks, best of %d" % reps}
+    # ---- the same solve through the C ABI (gpk_mg_create / gpk_mg_potrf_solve): ONE process drives all `world` GPUs with
+    # peer-to-peer panel puts; rank 0 runs it while the other ranks wait on a CPU (gloo) barrier, their GPUs idle
+    try:
+        cabi = {"what": "gpk_mg_potrf_solve: single process, round-robin block columns, cudaMemcpy2DAsync peer puts (no NCCL)",
+                "ndev": world, "nb": nb}
+        alpha_c = torch.zeros(n, dtype=torch.float64, device="cuda")
+        if rank == 0:
+            from gp_algos_b200.multi_gpu import MultiGpuGp
+            mg = MultiGpuGp(world, nb=nb)
+            runs = [mg.fit(X, y, theta) for _ in range(reps)]
+            mg.close()
+            f = min(runs, key=lambda r: r.seconds)
+            cabi.update({"seconds": f.seconds, "seconds_all": [r.seconds for r in runs],
+                         "potrf_tflops_per_gpu": float(n) ** 3 / 3 / f.seconds * 1e-12 / world, "ll": f.logLikelihood,
+                         "ll_rel_diff_vs_nccl_path": abs(f.logLikelihood - fit.logLikelihood) / abs(fit.logLikelihood),
+                         "bytes_put_to_peers": f.put_bytes})
+            alpha_c.copy_(torch.from_numpy(f.alphaVec))
+        if dist is not None:
+            dist.barrier(group=cpu_group)          # CPU-side wait: no NCCL kernel spins on the idle GPUs meanwhile
+            dist.broadcast(alpha_c, src=0)
+        cabi["residual_Kalpha_minus_y_over_y"] = solver.residual(y, alpha_c.cpu().numpy())
+        rec["c_abi"] = cabi
+    except Exception as e:
+        rec["c_abi"] = {"error": f"{type(e).__name__}: {e}"[:400]}
     del solver
     torch.cuda.empty_cache()
     return rec
@@ -358,8 +382,9 @@ def nccl_parity(dist, rank, world, local, g0, n=5000, nb=256):
 def run_sharded(h, dist, rank, world, local):
     rec = {}
     g0 = dist.new_group(ranks=[0]) if dist is not None else None     # rank 0 alone: the in-run single-GPU references
+    cpu_group = dist.new_group(backend="gloo") if dist is not None else None
     for name, fn in (("c4", lambda: bench_c4(h, dist, rank, world)),
-                     ("c5", lambda: bench_c5(dist, rank, world, local)),
+                     ("c5", lambda: bench_c5(dist, rank, world, local, cpu_group)),
                      ("nccl_parity", (lambda: nccl_parity(dist, rank, world, local, g0)) if world > 1 else None)):
         if fn is None:
             continue

@@ -7,11 +7,9 @@ and error behaviour), used by the parity tests and the benchmark:
     utils.KernelRequisites  ->  gp_algos_b200.kernel_requisites  (GaussianRbfParams, GaussianRbfKernel)
     gp.regression.Co2Prediction -> gp_algos_b200.co2_prediction  (Co2HyperParams, Co2Kernel: the second closed-form kernel)
     utils.MatrixUtils       ->  gp_algos_b200.matrix_utils       (buildKernelMatrix, forwardSolve, ...)
-    utils.StatsUtils        ->  gp_algos_b200.stats_utils        (host helpers of the callers: pnorm, mse, meanAndVarOfData, ...)
     gp.regression.GpPredictor -> gp_algos_b200.gp_predictor      (GpPredictor, PredictionInput, ...)
     gp.classification.*      ->  gp_algos_b200.ep_classification (EpParameterEstimator, GpClassifier, ...)
-    dynamicalsystems.filtering.{UnscentedKalmanFilter, GPUnscentedKalmanFilter} -> gp_algos_b200.gp_ukf
-    dynamicalsystems.filtering.{SsmExamples, SsmModel.generateSeries} -> gp_algos_b200.ssm_examples (host: test models + sampler)
+    dynamicalsystems.filtering.GPUnscentedKalmanFilter -> gp_algos_b200.gp_ukf (the whole filter run is one device call)
     gp.optimization.GPOptimizer -> gp_algos_b200.gp_optimizer    (GP-UCB inner loop on a resident model)
     (batched independent GPs and their rank sharding: gp_algos_b200.batched;
      one large GP over a 2-D block-cyclic GPU grid: gp_algos_b200.distributed)
@@ -24,15 +22,13 @@ from .co2_prediction import Co2HyperParams, Co2Kernel, co2DataToYearWithValue  #
 from .gp_predictor import GpPredictor, PredictionInput, PredictionTrainingInput, GaussianDistribution  # noqa: F401
 from . import matrix_utils as MatrixUtils  # noqa: F401
 from . import batched  # noqa: F401
-from . import stats_utils as StatsUtils  # noqa: F401
-from . import ssm_examples as SsmExamples  # noqa: F401
 from .ep_classification import (EpParameterEstimator, GpClassifier, MarginalLikelihoodEvaluator, SiteParams,  # noqa: F401
                                 AvgBasedStopCriterion, FixedSweeps, ClassifierInput, AfterEstimationClassifierInput,
                                 HyperParameterOptimInput, GradientHyperParamsOptimizer, ApacheCommonsOptimizer,
                                 MeshHyperParamsLogLikelihoodEvaluator, HyperParamsMeshValues)
 from .gp_optimizer import GPOptimizer, GPOInput, BreezeLbfgsOptimizer, ucb_with_gradient  # noqa: F401
-from .gp_ukf import (UnscentedKalmanFilter, GPUnscentedKalmanFilter, UnscentedTransformParams, UnscentedFilteringInput,  # noqa: F401
-                     SsmModel, FilteringOutput)
+from .gp_ukf import (GPUnscentedKalmanFilter, UnscentedTransformParams, UnscentedFilteringInput, SsmModel,  # noqa: F401
+                     FilteringOutput)
 from ._lib import GpkError, NotPositiveDefiniteError, MatrixNotSymmetricError, lib_path  # noqa: F401
 
 __all__ = ["GaussianRbfKernel", "GaussianRbfParams", "Co2Kernel", "Co2HyperParams", "GpPredictor", "PredictionInput", "PredictionTrainingInput",

@@ -90,6 +90,8 @@ def load():
         lib.gpk_gp_model_size.argtypes = [vp, vp]
         lib.gpk_gp_model_predict.argtypes = [vp, vp, vp, ci, _i64, ci, vp, vp, _i64, vp, _i64]
         lib.gpk_gp_models_mean.argtypes = [vp, vp, ci, vp, ci, _i64, vp]
+        lib.gpk_gp_models_mean_var.argtypes = [vp, vp, ci, vp, ci, _i64, vp, vp]
+        lib.gpk_gpukf_filter.argtypes = [vp, vp, ci, vp, ci, ci, ci, vp, vp, vp, cd, cd, cd, ci, vp, vp, vp]
         lib.gpk_gp_model_ucb.argtypes = [vp, vp, vp, ci, _i64, cd, vp, vp, _i64, vp, vp]
         lib.gpk_gp_predict.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, _i64, vp, ci, cd, vp, vp, _i64, vp]
         lib.gpk_potrf_inv_block_dev.argtypes = [vp, vp, vp, ci, vp]
@@ -104,6 +106,17 @@ def load():
         lib.gpk_gp_nll_grad_batched.argtypes = [vp, ci, vp, ci, ci, _i64, _i64, vp, vp, ci, cd, ci, vp, vp, vp]
         lib.gpk_gp_nll_grad_batched_dev.argtypes = [vp, ci, vp, ci, ci, _i64, _i64, vp, vp, ci, cd, ci, vp, vp]
         lib.gpk_gp_predict_batched.argtypes = [vp, ci, vp, ci, ci, _i64, _i64, vp, vp, vp, ci, _i64, _i64, ci, cd, vp, vp, vp, vp]
+        lib.gpk_mg_create.argtypes = [C.POINTER(vp), ci, vp]
+        lib.gpk_mg_destroy.argtypes = [vp]
+        lib.gpk_mg_last_error.argtypes = [vp]
+        lib.gpk_mg_last_error.restype = C.c_char_p
+        lib.gpk_mg_device_count.argtypes = [vp]
+        lib.gpk_mg_set_block.argtypes = [vp, ci]
+        lib.gpk_mg_potrf_solve.argtypes = [vp, vp, ci, ci, _i64, vp, vp, ci, cd, vp, vp, vp]
+        lib.gpk_mg_last_seconds.argtypes = [vp]
+        lib.gpk_mg_last_seconds.restype = cd
+        lib.gpk_mg_last_put_bytes.argtypes = [vp]
+        lib.gpk_mg_last_put_bytes.restype = C.c_int64
         _lib = lib
         return lib
 

@@ -102,9 +102,16 @@ class LockstepLbfgs:
     """R independent L-BFGS(m = 4, maxIter) minimisations advanced in lockstep: in every round each live instance proposes ONE
     point and all proposals are evaluated by ONE call of `batched_func(points[R', P], which[R']) -> (values[R'], grads[R', P])`
     -- for MLE restarts that is one gpk_gp_nll_grad_batched launch sequence for all restarts instead of R sequential
-    evaluations (GPOptimizer.scala:54-61 and the `obtainOptimalHyperParams` callers restart sequentially).  Per instance the
-    algorithm and the wrapper logic are those of BreezeLbfgsOptimizer (optimization/Optimization.scala:37-61: best-seen point,
-    one extra evaluation at the end); a non-finite value (failed factorisation) is treated as a rejected line-search step."""
+    evaluations (GPOptimizer.scala:54-61 and the `obtainOptimalHyperParams` callers restart sequentially).
+
+    What is and is not the reference's: the WRAPPER logic per instance is BreezeLbfgsOptimizer's (optimization/Optimization.scala:
+    37-61: best-seen point, one extra evaluation at the end point).  The inner iteration is this module's own: two-loop L-BFGS
+    with memory m, Armijo-only backtracking (sufficient decrease c1, halving; NO curvature / Wolfe condition), first step
+    1/max(1, |g|), stop at |g| <= 1e-9 max(1, |f|) or maxIter accepted steps.  Breeze's LBFGS uses a strong-Wolfe line search
+    and its own tolerances, so from the same start point this does NOT follow the trajectory of
+    GpPredictor.obtainOptimalHyperParams (nor does the reference pin that trajectory anywhere); every returned point is an exact
+    point of the same objective and never worse than its start.  A non-finite value (failed factorisation) is a rejected
+    line-search step; a restart that never saw a finite value returns its start point with value +inf (-inf from maximize)."""
 
     def __init__(self, maxIter: int = 20, m: int = 4, c1: float = 1e-4, maxLineSearch: int = 20):
         self.maxIter, self.m, self.c1, self.maxLineSearch = maxIter, m, c1, maxLineSearch
@@ -115,7 +122,7 @@ class LockstepLbfgs:
         X0 = np.array(initPoints, dtype=np.float64, copy=True)
         R, P = X0.shape
         st = [dict(x=X0[r].copy(), f=None, g=None, hist=[], d=None, slope=None, step=None, ls=0, it=0, phase="init",
-                   trial=X0[r].copy(), best_x=X0[r].copy(), best_v=np.finfo(float).max) for r in range(R)]
+                   trial=X0[r].copy(), best_x=X0[r].copy(), best_v=np.inf) for r in range(R)]
 
         def direction(s):
             g, hist = s["g"], s["hist"]
@@ -198,7 +205,8 @@ class LockstepLbfgs:
 def obtain_optimal_hyper_params_multistart(trainingData, targets, initThetas, sigmaNoise=None, maxIter: int = 20, handle=None):
     """GpPredictor.obtainOptimalHyperParams (GpPredictor.scala:126-142, optimizeNoise = true) from R start points at once: the
     restarts share the training set (strideX = 0) and every lockstep round is ONE batched objective+gradient call.
-    Returns (thetas[R, D+2], logLikelihood[R]) -- the best-seen point and value of every restart."""
+    Returns (thetas[R, D+2], logLikelihood[R]) -- the best-seen point and value of every restart; a restart whose kernel
+    matrix was never positive definite comes back as its start point with logLikelihood = -inf."""
     X = np.asarray(trainingData, dtype=np.float64)
     y = np.ascontiguousarray(targets, dtype=np.float64)
     init = np.atleast_2d(np.asarray(initThetas, dtype=np.float64))

@@ -216,16 +216,6 @@ __global__ void __launch_bounds__(256) ucb_grad_kernel(const double* __restrict_
 
 }  // namespace
 
-struct gpk_model_s {
-    int n, N, D;
-    int ldx;        // rows allocated for X (>= n; == N so that gpk_gp_model_append has room)
-    double* X;      // n x D, ld ldx
-    double* Li;     // N x N
-    double* alpha;  // N
-    double theta[GPK_MAX_D + 2];
-    ProblemParams pp;
-};
-
 namespace {
 
 int upload_model_x(gpk_handle h, gpk_model m, const double* X, int64_t ldx) {   // host n x D (ld ldx) -> device (ld m->ldx)
@@ -454,6 +444,7 @@ int gpk_gp_model_fit(gpk_handle h, const double* X, int n, int D, int64_t ldx, c
     if (rc) { gpk_gp_model_destroy(h, m); return rc; }
     // predictions never include the Option sigmaNoise in the kernel (GpPredictor.scala:31,36 use newKernelFunc only)
     m->pp.cp.extra_diag = 0.0;
+    m->has_s = has_s ? 1 : 0; m->s = has_s ? s : 0.0;     // remembered for gpk_gp_model_append
     if (ll) *ll = h->h_pinned[0];
     *out = m;
     return GPK_OK;
@@ -481,6 +472,7 @@ int gpk_gp_model_from_factor(gpk_handle h, const double* X, int n, int D, int64_
     if (!rc) rc = (cudaMemcpyAsync(m->alpha, alpha, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream) == cudaSuccess) ? 0 : GPK_ECUDA;
     if (!rc) rc = gpk_synchronize(h);
     if (rc) { gpk_gp_model_destroy(h, m); return rc; }
+    m->has_s = -1;                                         // unknown: the caller's factor may or may not include a sigmaNoise
     *out = m;
     return GPK_OK;
 }
@@ -490,6 +482,10 @@ int gpk_gp_model_from_factor(gpk_handle h, const double* X, int n, int D, int64_
 // is the old one bordered by one row, so the resident (L^-1, alpha) are updated in O(n^2): two triangular mat-vecs.
 int gpk_gp_model_append(gpk_handle h, gpk_model m, const double* x_new, double y_new, int has_s, double s, double* ll_delta) {
     if (!h || !m || !x_new) return gpk_set_error(h, GPK_EINVAL, "gpk_gp_model_append: bad arguments");
+    // the bordered row must carry the same Option sigmaNoise the factor was built with (GpPredictor.scala:116-117); a model
+    // adopted from a caller's factor (gpk_gp_model_from_factor) has none recorded and takes the caller's word
+    if (m->has_s >= 0 && ((has_s ? 1 : 0) != m->has_s || (has_s && s != m->s)))
+        return gpk_set_error(h, GPK_EINVAL, "gpk_gp_model_append: sigmaNoise differs from the one the model was fitted with");
     GPK_CUDA(h, cudaSetDevice(h->device));
     const int D = m->D;
     if (m->n == m->N) {   // no padding row left: move to a factor that is one tile larger

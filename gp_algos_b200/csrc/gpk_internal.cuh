@@ -186,6 +186,19 @@ struct ProblemParams {
 int gpk_make_cov_params(gpk_handle h, const double* theta, int D, int has_sigma_noise, double sigma_noise, CovParams* out);
 int gpk_make_problem_params(gpk_handle h, const double* theta, int D, int has_sigma_noise, double sigma_noise, ProblemParams* out);
 
+// a device-resident fitted GP (gpk_gp.cu creates / destroys it; gpk_ukf.cu reads it)
+struct gpk_model_s {
+    int n, N, D;
+    int ldx;        // rows allocated for X (>= n; == N so that gpk_gp_model_append has room)
+    double* X;      // n x D, ld ldx
+    double* Li;     // N x N
+    double* alpha;  // N
+    double theta[GPK_MAX_D + 2];
+    ProblemParams pp;
+    int has_s;      // Option sigmaNoise the model was fitted with (GpPredictor.scala:116-117) ...
+    double s;       // ... replayed by gpk_gp_model_append
+};
+
 // ---------------------------------------------------------------------------------------------
 // covariance (gpk_cov.cu)
 // ---------------------------------------------------------------------------------------------

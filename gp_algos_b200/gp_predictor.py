@@ -203,6 +203,19 @@ def models_mean(models, testData) -> np.ndarray:
     return out.T.copy()
 
 
+def models_mean_var(models, testData):
+    """Posterior means AND variances (diagonal of computePosterior's sigma, including noiseVar^2) of several resident models at
+    the same test rows in ONE device call -> two (len(testData), len(models)) arrays.  GPUnscentedKalmanFilter.scala:77-90
+    (means at the sigma points) and :138-147 (variances for the Q / R noise matrices)."""
+    Xs = _lib.fmat(np.atleast_2d(testData))
+    m, k = Xs.shape[0], len(models)
+    h = models[0].handle
+    arr = (C.c_void_p * k)(*[mdl._m for mdl in models])
+    mean = np.empty((k, m)); var = np.empty((k, m))
+    h.check(h.lib.gpk_gp_models_mean_var(h.h, arr, k, _lib.ptr(Xs), m, m, _lib.ptr(mean), _lib.ptr(var)))
+    return mean.T.copy(), var.T.copy()
+
+
 class FittedGp:
     """Opaque device token for (X, L^-1, alpha, theta) -- SURVEY.md 8(b) 'ownership'."""
 

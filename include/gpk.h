@@ -159,7 +159,9 @@ int gpk_gp_model_get_alpha(gpk_handle h, gpk_model m, double* alpha);
 /* gp/optimization/GPOptimizer.scala:48-71: each GP-UCB iteration adds ONE evaluated point (x_new: D doubles, y_new) to the
  * training set and the reference refits from scratch (preComputeComponents, :51).  This updates the resident L^-1 and alpha
  * by the bordered row instead (O(n^2)); afterwards the model equals gpk_gp_model_fit on the enlarged set with the same
- * hyper-parameters and the same Option sigmaNoise.  ll_delta (may be NULL) = logLikelihood(new set) - logLikelihood(old set).
+ * hyper-parameters and the same Option sigmaNoise; a (has_sigma_noise, sigma_noise) pair that differs from the one the model
+ * was fitted with is rejected with GPK_EINVAL (the bordered factor would be inconsistent).  ll_delta (may be NULL) =
+ * logLikelihood(new set) - logLikelihood(old set).
  * GPK_ENOTPD (gpk_last_info = n+1) when the enlarged matrix is not positive definite; the model is then unchanged. */
 int gpk_gp_model_append(gpk_handle h, gpk_model m, const double* x_new, double y_new, int has_sigma_noise,
                         double sigma_noise, double* ll_delta);
@@ -175,6 +177,27 @@ int gpk_gp_model_predict(gpk_handle h, gpk_model m, const double* Xs, int ms, in
  * for its mean at every sigma point; the reference does that with (2d+1) x dims computePosterior calls. */
 int gpk_gp_models_mean(gpk_handle h, const gpk_model* models, int nmodels, const double* Xs, int ms, int64_t ldxs,
                        double* mean);
+/* The same for means AND variances: var[j*ms + i] = diagonal of computePosterior's sigma of model j at row i (includes
+ * noiseVar^2, MatrixUtils.scala:63) -- the quantity GPUnscentedKalmanFilter.computeNoiseMatrix (:138-147) reads for the Q / R
+ * noise matrices, one computePosterior call per model in the reference.  var may be NULL. */
+int gpk_gp_models_mean_var(gpk_handle h, const gpk_model* models, int nmodels, const double* Xs, int ms, int64_t ldxs,
+                           double* mean, double* var);
+/* The GP-UKF filter run, device-resident: dynamicalsystems/filtering/UnscentedKalmanFilter.scala:24-80
+ * (inferHiddenState) with :82-118 (unscentedTransform, parameters alpha / beta / kappa) over the GP state-space model of
+ * GPUnscentedKalmanFilter.scala:63-103: transition x -> x + [mean_j(x)]_j over the d `sys_models` (one GP per state dimension,
+ * trained on z_t -> z_{t+1} - z_t), observation x -> [mean_j(x)]_j over the p `obs_models`, qNoise / rNoise = diag of the
+ * models' posterior variances at the previous hidden mean / the predicted mean.  Every model takes the d-dimensional state as
+ * input.  B independent series are filtered by the same launches and nothing crosses the host between time steps.
+ *   y            observations, series b: p x T column-major (Breeze DenseMatrix) at y + b*p*T
+ *   init_mean    d per series; init_cov: d x d column-major per series
+ *   hidden_means d x T column-major per series (column 0 = init_mean); hidden_covs: T matrices of d x d per series
+ *   ll           per series: sum_t log N(y_t; predicted observation mean, S_t) as KalmanFilter.marginalLogLikelihood computes it
+ *                (log of the density, -inf once the density underflows); may be NULL / compute_ll == 0.
+ * d, p <= 16.  GPK_ENOTPD when a covariance loses positive definiteness (breeze cholesky would throw NotConvergedException);
+ * gpk_last_info = 1 + t*B + b of the first such (time step, series). */
+int gpk_gpukf_filter(gpk_handle h, const gpk_model* sys_models, int d, const gpk_model* obs_models, int p, int B, int T,
+                     const double* y, const double* init_mean, const double* init_cov, double alpha, double beta, double kappa,
+                     int compute_ll, double* hidden_means, double* hidden_covs, double* ll);
 /* gp/optimization/GPOptimizer.scala:82-109 maximizeUCB's objective for ms candidate points (rows of Xs) at once:
  * ucb[i] = mean_i + k_param sqrt(sigma_i) and grad[i + d*ldg] = d ucb_i / d x_d
  *        = (dKs/dx) alpha + (0 - 2 (L^-1 dKs^t/dx)^t v) k_param / (2 sqrt(sigma_i)), Ks = k(x, X), v = L^-1 Ks^t
@@ -227,6 +250,30 @@ int gpk_gemv_dev(gpk_handle h, int trans, int m, int ncols, double alpha, const 
 int gpk_add_diag_dev(gpk_handle h, double* dA, int64_t ld, int n, double value);
 /* out_dev[0] (+)= sum_{i<n} log dA[i + i*ld]: the sum_i log L_ii term of GpPredictor.scala:147 for one diagonal block */
 int gpk_sum_log_diag_dev(gpk_handle h, const double* dA, int64_t ld, int n, double* out_dev, int accumulate);
+
+/* ---- one large GP on all GPUs of the node, behind the C ABI (BASELINE.json config 5) -------------------------
+ * Single process, no launcher: a JVM binds these like every other symbol.  gpk_mg_create opens `ndev` devices (devices == NULL:
+ * 0..ndev-1; ndev <= 0: all) with one libgpk handle, two bulk lanes and a put stream each and maps peer memory
+ * (cudaDeviceEnablePeerAccess: NVLink / NVSwitch on a B200 node).  gpk_mg_potrf_solve is GpPredictor.preComputeComponents +
+ * logLikelihood (GpPredictor.scala:104-124,144-149) for one training set: K is built block column by block column on the
+ * owning device from the replicated X (never communicated), factored right-looking with look-ahead 1 on a round-robin block-
+ * column layout (width gpk_mg_set_block, default 1024), each step's panel PUT into every peer's buffer by cudaMemcpy2DAsync over
+ * the peer mapping (no collective, event-ordered), alpha by a forward solve that rides along and a back solve over the owners.
+ * Outputs: alpha[n], ll, *info = 0 or the failing leading minor (GPK_ENOTPD).  Results on 1, 2, 4, 8 devices agree to rounding
+ * (the summation order of the trailing updates does not depend on the device count).
+ * The multi-PROCESS arrangement of the same algorithm (one process per GPU, 2-D block-cyclic, NCCL panel broadcasts) is
+ * gp_algos_b200/distributed.py over the *_dev building blocks above. */
+typedef struct gpk_mg_s* gpk_mg;
+int gpk_mg_create(gpk_mg* out, int ndev, const int* devices);
+int gpk_mg_destroy(gpk_mg mg);
+const char* gpk_mg_last_error(gpk_mg mg);
+int gpk_mg_device_count(gpk_mg mg);
+int gpk_mg_set_block(gpk_mg mg, int nb);
+int gpk_mg_potrf_solve(gpk_mg mg, const double* X, int n, int D, int64_t ldx, const double* y, const double* theta,
+                       int has_sigma_noise, double sigma_noise, double* alpha, double* ll, int* info);
+/* device time (CUDA events on device 0 around build + factor + solves) and bytes put to peers of the last solve */
+double gpk_mg_last_seconds(gpk_mg mg);
+int64_t gpk_mg_last_put_bytes(gpk_mg mg);
 
 /* ---- EP binary GP classification (BASELINE.json config 3) ------------------------------------------
  * gp/classification/EpParameterEstimator.scala:29-69 estimateSiteParams (+ :71-96 epMarginalLikelihood, :98-109

@@ -1,4 +1,4 @@
-"""Host mirror of dynamicalsystems/filtering/SsmExamples.scala and of SsmModel.generateSeries (SsmModel.scala:18-54): the two
+"""TEST HARNESS (not product code; SURVEY.md 2 marks the demo state-space models out of scope).  Host mirror of dynamicalsystems/filtering/SsmExamples.scala and of SsmModel.generateSeries (SsmModel.scala:18-54): the two
 benchmark state-space models of the reference's UKF / GP-UKF tests and the series sampler that feeds them.  Pure host code
 (scalar state); the mapping functions take a MATRIX of points, one per row, like every SsmModel of this package."""
 from __future__ import annotations
@@ -7,8 +7,8 @@ from typing import Optional
 
 import numpy as np
 
-from .gp_predictor import GaussianDistribution
-from .gp_ukf import SsmModel
+from gp_algos_b200.gp_predictor import GaussianDistribution
+from gp_algos_b200.gp_ukf import SsmModel
 
 
 def SinusoidalSsm() -> SsmModel:

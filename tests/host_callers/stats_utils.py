@@ -1,4 +1,4 @@
-"""Host mirror of utils/StatsUtils.scala: the small statistics helpers the callers of the hot path use (GPOptimizer's restart
+"""TEST HARNESS (not product code; SURVEY.md 2 marks StatsUtils out of scope).  Host mirror of utils/StatsUtils.scala: the small statistics helpers the callers of the hot path use (GPOptimizer's restart
 sampler, the GP-UKF scoring, Co2PredictionExecutor's error measure).  O(d^3) arithmetic on d x d matrices, d = state / input
 dimension -- host code in the reference and here; nothing n x n passes through this module.
 
@@ -11,7 +11,7 @@ import math
 
 import numpy as np
 
-from .gp_predictor import GaussianDistribution
+from gp_algos_b200.gp_predictor import GaussianDistribution
 
 
 def dnorm(x: float) -> float:                                  # StatsUtils.scala:15

@@ -168,7 +168,7 @@ def test_ctypes_bindings_match_the_header_prototypes():
     hdr = open(os.path.join(ROOT, "include", "gpk.h")).read()
     hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
     protos = {}
-    for m in re.finditer(r"\b(?:int|int64_t|const char\s*\*)\s+(gpk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+    for m in re.finditer(r"\b(?:int|int64_t|double|const char\s*\*)\s+(gpk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
         args = m.group(2).strip()
         protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
     assert len(protos) >= 40

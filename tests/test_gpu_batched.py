@@ -111,7 +111,6 @@ def test_c4_config_full_size_sampled_parity_and_partition_invariance():
     assert np.array_equal(ll_s, ll[lo:hi]) and np.array_equal(grad_s, grad[lo:hi])
 
 
-@pytest.mark.skipif(not os.environ.get("GPK_TEST_EXPERIMENTAL"), reason="written after the round's GPU budget was spent; first run next round")
 def test_multistart_hyperparameter_fit_in_lockstep():
     """batched.obtain_optimal_hyper_params_multistart: R restarts of GpPredictor.obtainOptimalHyperParams (GpPredictor.scala:126-142)
     advanced in lockstep, one batched objective call per round.  Every returned (theta, ll) is a point of the single-problem
@@ -125,3 +124,23 @@ def test_multistart_hyperparameter_fit_in_lockstep():
         ll_r, _ = orc.fast_loglik_with_derivs(X, y, thetas[r], None, 0)
         ll_0, _ = orc.fast_loglik_with_derivs(X, y, starts[r], None, 0)
         assert abs(ll_r - lls[r]) <= 1e-9 * abs(ll_r) and lls[r] >= ll_0 - 1e-9 * abs(ll_0)
+    # against R sequential single-start fits (GpPredictor.obtainOptimalHyperParams, GpPredictor.scala:126-142): the lockstep
+    # optimiser is not Breeze's (Armijo backtracking, its own stop rule), so only the outcome is compared: given enough
+    # iterations the best restart reaches the best sequential fit's likelihood to 0.1 %
+    thetas, lls = batched.obtain_optimal_hyper_params_multistart(X, y, starts, maxIter=40)
+    import gp_algos_b200 as gp
+    best_seq = -np.inf
+    for r in range(5):
+        kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(starts[r][0], starts[r][1:-1], starts[r][-1]))
+        pred = gp.GpPredictor(kf)
+        hp = pred.obtainOptimalHyperParams(X, None, y, True)
+        best_seq = max(best_seq, pred.logLikelihoodWithDerivatives(gp.PredictionTrainingInput(X, None, y), hp, 0)[0])
+    assert lls.max() >= best_seq - 1e-3 * abs(best_seq)
+
+
+def test_multistart_restart_that_is_never_positive_definite_reports_minus_infinity():
+    X, y, th = orc.make_c2(n=200, D=3, seed=22)
+    X[1] = X[0]                                                   # duplicate row + zero noise: K is singular at this start
+    bad = th.copy(); bad[-1] = 0.0
+    thetas, lls = batched.obtain_optimal_hyper_params_multistart(X, y, np.stack([th, bad]), maxIter=3)
+    assert np.isfinite(lls[0]) and lls[1] == -np.inf and np.array_equal(thetas[1], bad)

@@ -109,3 +109,22 @@ def test_append_not_positive_definite_leaves_the_model_unchanged():
     L, alpha = orc.lit_precompute(np.vstack([X, [[1.1, -0.4]]]), np.append(y, 0.3), th)
     assert np.all(np.abs(model.alphaVec - alpha) <= 1e-9 * np.abs(alpha).max())
     model.close()
+
+
+def test_append_rejects_a_sigma_noise_other_than_the_fitted_one():
+    """include/gpk.h: the bordered row must carry the Option sigmaNoise the factor was built with; anything else is GPK_EINVAL
+    (a C caller that forgets it would otherwise get an inconsistent factor without an error)."""
+    import ctypes as C
+    X, y, th = orc.make_c2(n=100, D=2, seed=9)
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
+    model = gp.GpPredictor(kf).fit(X[:90], 0.05, y[:90], th)
+    h = model.handle
+    x = np.ascontiguousarray(X[90]); d = C.c_double()
+    from gp_algos_b200 import _lib
+    for has_s, s in ((0, 0.0), (1, 0.06)):
+        rc = h.lib.gpk_gp_model_append(h.h, model._m, _lib.ptr(x), float(y[90]), has_s, s, C.addressof(d))
+        assert rc == _lib.GPK_EINVAL
+    model.append(X[90], y[90])                           # the Python mirror replays the stored value
+    L, alpha = orc.lit_precompute(X[:91], y[:91], th, 0.05)
+    assert np.allclose(model.alphaVec, alpha, rtol=1e-9, atol=1e-12)
+    model.close()

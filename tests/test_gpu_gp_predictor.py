@@ -227,6 +227,24 @@ def test_maximum_feature_dimension_and_beyond():
         _pred(th65).logLikelihoodWithDerivatives(gp.PredictionTrainingInput(X65, None, y[:50]), th65, 67)
 
 
+def test_one_handle_sees_growing_feature_dimensions():
+    """A FRESH handle evaluates D = 50 first and D = 60, 64 afterwards: the gradient kernel's dynamic shared memory (1024 D
+    bytes) must have been opted in for the largest D at the first request above 48 KB, not for that request's size."""
+    from gp_algos_b200 import _lib
+    h = _lib.Handle(0)
+    rng = np.random.default_rng(50)
+    for D in (50, 60, 64, 49):
+        n = 200
+        X = rng.uniform(size=(n, D)); y = np.sin(X[:, 0] * 3) + 0.1 * rng.standard_normal(n)
+        th = orc.pack_theta(1.1, np.linspace(2.0, 4.0, D), 0.2)
+        kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
+        ll, g = gp.GpPredictor(kf, handle=h).logLikelihoodWithDerivatives(gp.PredictionTrainingInput(X, None, y), th, D + 2)
+        llo, go = orc.fast_loglik_with_derivs(X, y, th)
+        assert abs(ll - llo) <= RTOL * abs(llo)
+        assert_grad(g, go)
+    h.close()
+
+
 def test_randomised_shapes_and_hyperparameters_sweep():
     """40 seeded random problems (n in 1..700 across the 128-padding boundaries, D in 1..12, random theta and Option sigmaNoise):
     objective, gradient and predictive moments against the LAPACK-backed oracle."""

@@ -5,7 +5,7 @@ import math
 import numpy as np
 import pytest
 
-from gp_algos_b200 import stats_utils as su
+from tests.host_callers import stats_utils as su
 from gp_algos_b200.gp_predictor import GaussianDistribution
 from oracle import gp_oracle as orc
 

@@ -1,10 +1,12 @@
-"""CPU: host logic of the GP-UKF mirror (gp_algos_b200/gp_ukf.py) -- the unscented transform against the oracle's restatement
+"""CPU: the host UKF recursion of the test harness (tests/host_callers/ukf_host.py) -- the unscented transform against the oracle's restatement
 of UnscentedKalmanFilter.scala:82-118, and the recursion on a linear-Gaussian model, where the UKF must reproduce the
 Kalman filter exactly (a property the reference's own UKF tests rely on).  No GPU: the SSM functions here are plain NumPy."""
 import numpy as np
 
 import gp_algos_b200 as gp
-from gp_algos_b200.gp_ukf import logGaussianDensity, nllOfHiddenData
+from tests.host_callers.stats_utils import logGaussianDensity, nllOfHiddenData
+from tests.host_callers import stats_utils as StatsUtils
+from tests.host_callers.ukf_host import UnscentedKalmanFilter
 from oracle import gp_oracle as orc
 
 
@@ -12,7 +14,7 @@ def test_unscented_transform_matches_oracle_restatement():
     rng = np.random.default_rng(0)
     A = rng.standard_normal((3, 3)); cov = A @ A.T + 0.5 * np.eye(3); mean = rng.standard_normal(3)
     f = lambda p: np.array([np.sin(p[0]) + p[1], p[1] * p[2], p[0] - p[2] ** 2, 1.0 + p[0]])
-    ukf = gp.UnscentedKalmanFilter()
+    ukf = UnscentedKalmanFilter()
     for (a, b, k) in ((1.0, 0.0, 2.0), (0.5, 2.0, 1.0)):
         out = ukf.unscentedTransform(gp.GaussianDistribution(mean, cov), gp.UnscentedTransformParams(a, b, k),
                                      lambda pts: np.stack([f(p) for p in pts]))
@@ -35,7 +37,7 @@ def test_ukf_on_a_linear_gaussian_model_is_the_kalman_filter():
             z[:, t + 1] = F @ z[:, t] + rng.multivariate_normal(np.zeros(2), Q)
     model = gp.SsmModel(transitionFuncImpl=lambda u, pts, t: np.atleast_2d(pts) @ F.T, observationFuncImpl=lambda pts, t: np.atleast_2d(pts) @ H.T)
     inp = gp.UnscentedFilteringInput(model, y, None, np.array([1.0, -1.0]), 0.2 * np.eye(2), lambda ctx: Q, lambda ctx: R)
-    out = gp.UnscentedKalmanFilter().inferHiddenState(inp, None, True)
+    out = UnscentedKalmanFilter().inferHiddenState(inp, None, True)
     m, P, ll = np.array([1.0, -1.0]), 0.2 * np.eye(2), 0.0
     for t in range(1, T):                                   # textbook Kalman filter
         mp, Pp = F @ m, F @ P @ F.T + Q
@@ -57,7 +59,7 @@ def test_ukf_on_a_linear_gaussian_model_is_the_kalman_filter():
 
 # ---- the facts the reference's own src/test/scala/dynamicalsystems/filtering/UnscentedKalmanFilterTest.scala holds -----------
 def test_reference_unscented_transform_facts():
-    ukf = gp.UnscentedKalmanFilter()
+    ukf = UnscentedKalmanFilter()
     # :44-56  1-d Gaussian through the identity
     tr = ukf.unscentedTransform(gp.GaussianDistribution(np.array([2.]), np.array([[2.]])), gp.UnscentedTransformParams(), lambda pts: pts)
     assert tr.distribution.dim == 1 and tr.distribution.sigma[0, 0] != 0.0
@@ -74,7 +76,7 @@ def test_reference_unscented_transform_facts():
 
 
 def test_reference_filter_facts_on_the_sinusoidal_and_kitagawa_models():
-    from gp_algos_b200.ssm_examples import SinusoidalSsm, KitagawaSsm, generateSeries
+    from tests.host_callers.ssm_examples import SinusoidalSsm, KitagawaSsm, generateSeries
     rng = np.random.default_rng(11)
     seq = 50
     cases = ((SinusoidalSsm(), gp.GaussianDistribution(np.array([0.]), np.array([[1.]]))),          # GaussianDistribution.standard (:29)
@@ -85,7 +87,7 @@ def test_reference_filter_facts_on_the_sinusoidal_and_kitagawa_models():
         inp = gp.UnscentedFilteringInput(model, obs, None, init.mean, init.sigma, lambda ctx, m=model: m.latentNoise,
                                          lambda ctx, m=model: m.obsNoise)
         for params in (gp.UnscentedTransformParams(alpha=1.0), gp.UnscentedTransformParams(2.012, 0.24, 0.4871)):   # :82-86, :97-99
-            out = gp.UnscentedKalmanFilter().inferHiddenState(inp, params, True)
+            out = UnscentedKalmanFilter().inferHiddenState(inp, params, True)
             assert out.hiddenMeans.shape[1] == seq and out.hiddenMeans.shape[0] == hidden.shape[0] and len(out.hiddenCovs) == seq
             assert np.all(np.isfinite(out.hiddenMeans))
             # (the reference asserts shapes only: on the bimodal Kitagawa model the filter may lose track and the likelihood,
@@ -95,5 +97,5 @@ def test_reference_filter_facts_on_the_sinusoidal_and_kitagawa_models():
     model, init = cases[0]
     hidden, obs = generateSeries(model, 200, init, np.random.default_rng(12))
     inp = gp.UnscentedFilteringInput(model, obs, None, init.mean, init.sigma, lambda ctx: model.latentNoise, lambda ctx: model.obsNoise)
-    out = gp.UnscentedKalmanFilter().inferHiddenState(inp, gp.UnscentedTransformParams(alpha=1.0), True)
-    assert gp.StatsUtils.mse(out.hiddenMeans[:, 1:].T, hidden[:, 1:].T) < gp.StatsUtils.mse(np.zeros_like(hidden[:, 1:].T), hidden[:, 1:].T)
+    out = UnscentedKalmanFilter().inferHiddenState(inp, gp.UnscentedTransformParams(alpha=1.0), True)
+    assert StatsUtils.mse(out.hiddenMeans[:, 1:].T, hidden[:, 1:].T) < StatsUtils.mse(np.zeros_like(hidden[:, 1:].T), hidden[:, 1:].T)
