@@ -260,7 +260,7 @@ int potrf_nb() {     // block-column width of the factor-only driver (gpk_potrf_
 }  // namespace
 
 int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev,
-                            cudaEvent_t* kinv_done, int factor_only) {
+                            cudaEvent_t* kinv_done, int factor_only, double* rhsB, double* rhsV, int rhsM) {
     const int nbk = factor_only ? potrf_nb() : pipe_nb();
     const int nt = (N + nbk - 1) / nbk;
     auto bs = [&](int k) { return k * nbk < N ? k * nbk : N; };
@@ -272,7 +272,7 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     cudaEvent_t ev = next_event(h);
     GPK_CUDA(h, cudaEventRecord(ev, M));            // K is built (and earlier users of the buffers are done) before S/S2 start
     GPK_CUDA(h, cudaStreamWaitEvent(S, ev, 0));
-    if (!factor_only) GPK_CUDA(h, cudaStreamWaitEvent(S2, ev, 0));
+    if (!factor_only || rhsB) GPK_CUDA(h, cudaStreamWaitEvent(S2, ev, 0));
     if (Kinv) GPK_CUDA(h, cudaStreamWaitEvent(S3, ev, 0));   // (a stream that is forked must also be joined: graph capture insists)
     cudaEvent_t evGcol_prev = nullptr;              // S finished block column k+1 of trailing update k-1
     cudaEvent_t evLi = nullptr;                     // S2 finished the last row of L^-1
@@ -286,6 +286,7 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
         cudaEvent_t evF = next_event(h);
         GPK_CUDA(h, cudaEventRecord(evF, M));
         tr.mark(M, "M:F", k);
+        cudaEvent_t evPanel = nullptr;                  // panel k (staged in Li's slots) is complete
         if (k + 1 < nt) {
             const int b1 = bs(k + 1), s1 = bs(k + 2) - b1;
             GemmDesc g = gemm_desc();                                                                                // P_k
@@ -301,6 +302,7 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
             }
             cudaEvent_t evE = next_event(h);
             GPK_CUDA(h, cudaEventRecord(evE, M));
+            evPanel = evE;
             if (evGcol_prev) GPK_CUDA(h, cudaStreamWaitEvent(M, evGcol_prev, 0));
             tr.mark(M, "M:P", k);
             rc = col_update(h, A, Li, N, bk, sk, b1, s1);                                                            // U_k(:,k+1)
@@ -321,6 +323,29 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
                     if (rc) return rc;
                 }
                 tr.mark(S, "S:U", k);
+            }
+        }
+        if (factor_only && rhsB) {
+            // right-hand sides riding along (forward substitution V = L^-1 B, block row by block row, on the bulk stream S2):
+            //   V_k = L_kk^-1 B_k ;  B_i -= L_ik V_k for i > k   -- n^2 M flops of full-GPU GEMMs that fill the spine's gaps
+            GPK_CUDA(h, cudaStreamWaitEvent(S2, evF, 0));
+            StreamSwap swr(h, S2);
+            GemmDesc g = gemm_desc();
+            g.P = rhsB + bk; g.ldp = N; g.p_kcontig = 1;                        // P(r,q) = B(bk+q, r)
+            g.Q = Li + bk + (int64_t)bk * N; g.ldq = N; g.q_kcontig = 0;        // Q(s,q) = Li_kk(s,q), zero for q > s
+            g.D = rhsV + bk; g.ldd = N; g.R = rhsM; g.S = sk; g.K = sk; g.ke_s = 1; g.heavy_last = 1;
+            rc = gpk_gemm(h, g);
+            if (rc) return rc;
+            if (k + 1 < nt) {
+                const int b1 = bs(k + 1);
+                GPK_CUDA(h, cudaStreamWaitEvent(S2, evPanel, 0));
+                g = gemm_desc();
+                g.P = rhsV + bk; g.ldp = N; g.p_kcontig = 1;                    // P(r,q) = V(bk+q, r)
+                g.Q = Li + b1 + (int64_t)bk * N; g.ldq = N; g.q_kcontig = 0;    // Q(s,q) = L(b1+s, bk+q)
+                g.D = rhsB + b1; g.ldd = N; g.Cin = g.D; g.ldc = N;
+                g.R = rhsM; g.S = N - b1; g.K = sk; g.alpha = -1.0; g.beta = 1.0;
+                rc = gpk_gemm(h, g);
+                if (rc) return rc;
             }
         }
         if (factor_only) continue;     // only L (and the diagonal-block inverses the panels were solved with) is wanted
@@ -378,7 +403,14 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     cudaEvent_t e1 = next_event(h), e2 = next_event(h);
     GPK_CUDA(h, cudaEventRecord(e1, S));
     GPK_CUDA(h, cudaStreamWaitEvent(M, e1, 0));
-    if (factor_only) return GPK_OK;
+    if (factor_only) {
+        if (rhsB) {
+            cudaEvent_t e3 = next_event(h);
+            GPK_CUDA(h, cudaEventRecord(e3, S2));
+            GPK_CUDA(h, cudaStreamWaitEvent(M, e3, 0));
+        }
+        return GPK_OK;
+    }
     GPK_CUDA(h, cudaEventRecord(e2, Kinv ? S3 : S2));   // no K^-1 requested: S3 was never forked, join the row chain
     if (kinv_done && Kinv && evLi) {
         GPK_CUDA(h, cudaStreamWaitEvent(M, evLi, 0));
@@ -390,12 +422,173 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
     return GPK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Factor-only look-ahead driver (gpk_potrf_factor / gpk_potrf_factor_solve).  Without the inverse rows and the K^-1
+// accumulation there are only n^3/3 flops of bulk work to hide the serial spine behind, so the spine itself is cut to what
+// the NEXT diagonal block needs: per step k the handle's stream runs
+//     F_k            L_kk, L_kk^-1                      (recursion on the nb x nb diagonal block)
+//     Pc_k           L_{k+1,k} = A_{k+1,k} L_kk^-T      (ONE block row of the panel)
+//     Uc_k           A_{k+1,k+1} -= L_{k+1,k} L_{k+1,k}^t   (ONE diagonal block)
+// and nothing else; a medium-priority stream S1 solves the rest of the panel (Pr_k) and finishes block column k+1 (Ur_k),
+// the low-priority stream S updates block column k+2 first (the next step's Uc / Ur wait for it) and then everything to the
+// right of it.  Optional right-hand sides ride along on a fourth stream (forward substitution V = L^-1 B).
+// Hazards: every region of A is written by one stream at a time -- Uc_k / Ur_k wait for S's column-first launch of step k-1,
+// Pc_{k+1} waits for Ur_k, Pr_{k+1} follows Ur_k in stream order, S's launches are in order.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// A[r0.., bj..bj+sj) -= Lst[r0.., bk..) Lst[bj.., bk..)^t with L staged in Li's slots; nrows rows from r0; tri: the block starts
+// on the diagonal (r0 == bj) and only its lower tiles are wanted
+int stage_update(gpk_handle h, double* A, const double* Li, int N, int bk, int sk, int bj, int sj, int r0, int nrows, int tri) {
+    if (nrows <= 0 || sj <= 0) return GPK_OK;
+    GemmDesc g = gemm_desc();
+    g.P = Li + bj + (int64_t)bk * N; g.ldp = N;
+    g.Q = Li + r0 + (int64_t)bk * N; g.ldq = N;
+    g.D = A + r0 + (int64_t)bj * N; g.ldd = N; g.Cin = g.D; g.ldc = N;
+    g.R = sj; g.S = nrows; g.K = sk; g.alpha = -1.0; g.beta = 1.0; g.tri_out = tri;
+    return gpk_gemm(h, g);
+}
+
+// rows [r0, r1) of panel k: Lst = A L_kk^-T into Li's slots, then copied back into A (the factor is returned in A)
+int stage_panel(gpk_handle h, double* A, double* Li, int N, int bk, int sk, int r0, int r1) {
+    if (r1 <= r0) return GPK_OK;
+    GemmDesc g = gemm_desc();
+    g.P = Li + bk + (int64_t)bk * N; g.ldp = N; g.p_kcontig = 0;
+    g.Q = A + r0 + (int64_t)bk * N; g.ldq = N; g.q_kcontig = 0;
+    g.D = Li + r0 + (int64_t)bk * N; g.ldd = N;
+    g.R = sk; g.S = r1 - r0; g.K = sk; g.ke_r = 1; g.heavy_last = 1;
+    int rc = gpk_gemm(h, g);
+    if (rc) return rc;
+    return gpk_copy2d(h, A + r0 + (int64_t)bk * N, N, Li + r0 + (int64_t)bk * N, N, r1 - r0, sk);
+}
+
+int potrf_factor_pipelined(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev, double* rhsB, double* rhsV,
+                           int rhsM) {
+    const int nbk = potrf_nb();
+    const int nt = (N + nbk - 1) / nbk;
+    auto bs = [&](int k) { return k * nbk < N ? k * nbk : N; };
+    GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
+    Ctx c{h, N, N, 1, info_dev, 1, (int64_t)N * N, 0, 0};
+    cudaStream_t M = h->stream, S = h->pipe[0], S1 = h->side[GPK_NSIDE - 1], R = h->pipe[1];
+    cudaEvent_t ev0 = next_event(h);
+    GPK_CUDA(h, cudaEventRecord(ev0, M));
+    GPK_CUDA(h, cudaStreamWaitEvent(S, ev0, 0));
+    GPK_CUDA(h, cudaStreamWaitEvent(S1, ev0, 0));
+    if (rhsB) GPK_CUDA(h, cudaStreamWaitEvent(R, ev0, 0));
+    cudaEvent_t evUr_prev = nullptr;                 // S1 finished block column k (rows below block row k) of update k-1
+    cudaEvent_t evG_next = nullptr;                  // S's column-first launch of step k-1: block column k+1 has updates <= k-1
+    int rc;
+    for (int k = 0; k < nt; ++k) {
+        const int bk = bs(k), sk = bs(k + 1) - bk;
+        rc = potrf_inv_rec(c, A + bk + (int64_t)bk * N, Li + bk + (int64_t)bk * N, T, sk, bk, 0);                   // F_k
+        if (rc) return rc;
+        cudaEvent_t evF = next_event(h);
+        GPK_CUDA(h, cudaEventRecord(evF, M));
+        cudaEvent_t evPc = nullptr, evPr = nullptr, evG_this = nullptr;
+        if (k + 1 < nt) {
+            const int b1 = bs(k + 1), b2 = bs(k + 2), s1 = b2 - b1;
+            if (evUr_prev) GPK_CUDA(h, cudaStreamWaitEvent(M, evUr_prev, 0));
+            rc = stage_panel(h, A, Li, N, bk, sk, b1, b2);                                                           // Pc_k
+            if (rc) return rc;
+            evPc = next_event(h);
+            GPK_CUDA(h, cudaEventRecord(evPc, M));
+            if (evG_next) GPK_CUDA(h, cudaStreamWaitEvent(M, evG_next, 0));
+            rc = stage_update(h, A, Li, N, bk, sk, b1, s1, b1, s1, 1);                                               // Uc_k
+            if (rc) return rc;
+            evUr_prev = nullptr;
+            if (k + 2 < nt) {
+                {
+                    GPK_CUDA(h, cudaStreamWaitEvent(S1, evF, 0));
+                    StreamSwap sw(h, S1);
+                    rc = stage_panel(h, A, Li, N, bk, sk, b2, N);                                                    // Pr_k
+                    if (rc) return rc;
+                    evPr = next_event(h);
+                    GPK_CUDA(h, cudaEventRecord(evPr, S1));
+                    GPK_CUDA(h, cudaStreamWaitEvent(S1, evPc, 0));
+                    if (evG_next) GPK_CUDA(h, cudaStreamWaitEvent(S1, evG_next, 0));
+                    rc = stage_update(h, A, Li, N, bk, sk, b1, s1, b2, N - b2, 0);                                   // Ur_k
+                    if (rc) return rc;
+                    evUr_prev = next_event(h);
+                    GPK_CUDA(h, cudaEventRecord(evUr_prev, S1));
+                }
+                {
+                    GPK_CUDA(h, cudaStreamWaitEvent(S, evPc, 0));
+                    GPK_CUDA(h, cudaStreamWaitEvent(S, evPr, 0));
+                    StreamSwap sw(h, S);
+                    const int b3 = bs(k + 3);
+                    rc = col_update(h, A, Li, N, bk, sk, b2, b3 - b2);                                               // U_k(:, k+2)
+                    if (rc) return rc;
+                    evG_this = next_event(h);
+                    GPK_CUDA(h, cudaEventRecord(evG_this, S));
+                    if (k + 3 < nt) {
+                        rc = col_update(h, A, Li, N, bk, sk, b3, N - b3);                                            // U_k(k+3:, k+3:)
+                        if (rc) return rc;
+                    }
+                }
+            }
+            evG_next = evG_this;
+        }
+        if (rhsB) {
+            // right-hand sides riding along: V_k = L_kk^-1 B_k ;  B_i -= L_ik V_k for i > k
+            GPK_CUDA(h, cudaStreamWaitEvent(R, evF, 0));
+            StreamSwap swr(h, R);
+            GemmDesc g = gemm_desc();
+            g.P = rhsB + bk; g.ldp = N; g.p_kcontig = 1;                        // P(r,q) = B(bk+q, r)
+            g.Q = Li + bk + (int64_t)bk * N; g.ldq = N; g.q_kcontig = 0;        // Q(s,q) = Li_kk(s,q), zero for q > s
+            g.D = rhsV + bk; g.ldd = N; g.R = rhsM; g.S = sk; g.K = sk; g.ke_s = 1; g.heavy_last = 1;
+            rc = gpk_gemm(h, g);
+            if (rc) return rc;
+            if (k + 1 < nt) {
+                const int b1 = bs(k + 1);
+                GPK_CUDA(h, cudaStreamWaitEvent(R, evPc, 0));
+                if (evPr) GPK_CUDA(h, cudaStreamWaitEvent(R, evPr, 0));
+                g = gemm_desc();
+                g.P = rhsV + bk; g.ldp = N; g.p_kcontig = 1;                    // P(r,q) = V(bk+q, r)
+                g.Q = Li + b1 + (int64_t)bk * N; g.ldq = N; g.q_kcontig = 0;    // Q(s,q) = L(b1+s, bk+q)
+                g.D = rhsB + b1; g.ldd = N; g.Cin = g.D; g.ldc = N;
+                g.R = rhsM; g.S = N - b1; g.K = sk; g.alpha = -1.0; g.beta = 1.0;
+                rc = gpk_gemm(h, g);
+                if (rc) return rc;
+            }
+        }
+    }
+    cudaEvent_t e1 = next_event(h), e2 = next_event(h);
+    GPK_CUDA(h, cudaEventRecord(e1, S));
+    GPK_CUDA(h, cudaStreamWaitEvent(M, e1, 0));
+    GPK_CUDA(h, cudaEventRecord(e2, S1));
+    GPK_CUDA(h, cudaStreamWaitEvent(M, e2, 0));
+    if (rhsB) {
+        cudaEvent_t e3 = next_event(h);
+        GPK_CUDA(h, cudaEventRecord(e3, R));
+        GPK_CUDA(h, cudaStreamWaitEvent(M, e3, 0));
+    }
+    return GPK_OK;
+}
+
+}  // namespace
+
 // Factor only (LAPACK dpotrf 'L': GpPredictor.scala:120, EpParameterEstimator.scala:58 when the caller wants nothing but L): the
 // look-ahead driver without the inverse rows and the K^-1 accumulation -- n^3/3 flops instead of n^3.  Only the diagonal
 // blocks are inverted (the panels are solved as GEMMs with them).  Li is still an N x N staging area.
 int gpk_potrf_factor(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev) {
-    if (N >= 2 * potrf_nb()) return gpk_potrf_inv_pipelined(h, A, Li, nullptr, T, N, 1, info_dev, nullptr, 1);
+    if (N >= 2 * potrf_nb()) return potrf_factor_pipelined(h, A, Li, T, N, info_dev, nullptr, nullptr, 0);
     return gpk_potrf_inv(h, A, Li, T, N, 1, info_dev, 1);
+}
+
+// Factor + multi-right-hand-side forward solve: A -> L (in place), V = L^-1 B for B, V: N x M (ld N, M a multiple of 128); B is
+// destroyed.  EP's posterior re-factorisation (EpParameterEstimator.scala:58-59: cholesky, then forwardSolve with n right-hand
+// sides) is this call.  Large N: the look-ahead driver with the right-hand sides riding along (no L^-1 is ever formed:
+// n^3/3 + n^2 M flops); small N: L^-1 by the recursion and one GEMM.
+int gpk_potrf_factor_solve(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev, double* B, double* V, int M) {
+    if (N >= 2 * potrf_nb())
+        return potrf_factor_pipelined(h, A, Li, T, N, info_dev, B, V, M);
+    int rc = gpk_potrf_inv(h, A, Li, T, N, 1, info_dev, 1);
+    if (rc) return rc;
+    GemmDesc g = gemm_desc();                                       // V = L^-1 B: C(m,c) = sum_{k<=m} Li(m,k) B(k,c)
+    g.P = B; g.ldp = N; g.p_kcontig = 1;
+    g.Q = Li; g.ldq = N; g.q_kcontig = 0;
+    g.D = V; g.ldd = N; g.R = M; g.S = N; g.K = N; g.ke_s = 1; g.heavy_last = 1;
+    return gpk_gemm(h, g);
 }
 
 bool gpk_use_pipelined(int N, int batch) { return batch == 1 && pipe_min() > 0 && N >= pipe_min() && N >= 2 * pipe_nb(); }

@@ -233,7 +233,10 @@ bool gpk_use_pipelined(int N, int batch);
 // kinv_done != nullptr: returns without waiting for the K^-1 accumulation; the caller must cudaStreamWaitEvent(*kinv_done)
 // (when non-null) on its stream before reading Kinv.
 int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev,
-                            cudaEvent_t* kinv_done = nullptr, int factor_only = 0);
+                            cudaEvent_t* kinv_done = nullptr, int factor_only = 0, double* rhsB = nullptr, double* rhsV = nullptr,
+                            int rhsM = 0);
+// A -> L in place and V = L^-1 B (B, V: N x M, ld N; B destroyed); Li: N x N staging (holds L^-1 only when N is small)
+int gpk_potrf_factor_solve(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev, double* B, double* V, int M);
 // L only (plus the inverses of the diagonal blocks, left in Li's diagonal blocks): n^3/3 flops.  Li: N x N staging.
 int gpk_potrf_factor(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev);
 // X = Lw^-1 B (backward == 0) or Lw^-t B (backward != 0) by blocked substitution on the padded lower factor Lw (N x N, ld N).

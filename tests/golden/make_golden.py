@@ -100,6 +100,20 @@ def c4_small(B=6, n=192, D=8, m=17):
     np.savez(os.path.join(HERE, "c4_small.npz"), B=B, **out)
 
 
+def c3_full(n=4096, D=4, sweeps=3):
+    """BASELINE.json config 3 at FULL size (n = 4096, D = 4, seed 3): three fixed EP sweeps by the LAPACK-backed
+    oracle (fast_ep_estimate: the reference's site loop with full rank-1 downdates, ~2.7 TB of memory traffic per sweep -- about
+    a quarter of an hour on the build container's cores, which is why it is generated once and committed: tau, nu, mu, cavity
+    parameters, diag L and logZ, 230 KB).  Run with `python tests/golden/make_golden.py c3_full`."""
+    X, t, th = orc.make_c3(n=n, D=D, seed=3)
+    K = orc.fast_build_kernel_matrix(X, th)
+    o = orc.fast_ep_estimate(K, t, fixed_sweeps=sweeps)
+    o2 = dict(o)
+    np.savez_compressed(os.path.join(HERE, "c3_full.npz"), n=n, D=D, sweeps=sweeps, theta=th, tau=o["tau"], nu=o["nu"], mu=o["mu"],
+                        cav_tau=o["cav_tau"], cav_nu=o["cav_nu"], diagL=np.diag(o["L"]).copy(), logZ=o["logZ"],
+                        x_checksum=float(X.sum()), t_checksum=int(t.sum()))
+
+
 def boston_soft():
     data = np.loadtxt(os.path.join(REF, "boston.csv"))
     res = np.loadtxt(os.path.join(REF, "boston", "bostonPredResults.txt"))
@@ -147,6 +161,9 @@ def co2_maunaloa():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "c3_full":
+        c3_full()
+        sys.exit(0)
     mu_3x3(); c1_small(); c2_small(); c3_small(); c3_grad_small(); c4_small()
     if os.path.isdir(REF):
         boston_soft()
