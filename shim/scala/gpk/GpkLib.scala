@@ -56,6 +56,10 @@ trait GpkLib extends Library {
   def gpk_gp_models_mean(h: Pointer, models: Array[Pointer], nmodels: Int, xs: Array[Double], ms: Int, ldxs: Long, mean: Array[Double]): Int
   def gpk_gp_models_mean_var(h: Pointer, models: Array[Pointer], nmodels: Int, xs: Array[Double], ms: Int, ldxs: Long,
                              mean: Array[Double], variance: Array[Double]): Int
+  // GP-UKF filter run, device-resident, B series at once (UnscentedKalmanFilter.scala:24-118 over GPUnscentedKalmanFilter.scala:63-103)
+  def gpk_gpukf_filter(h: Pointer, sysModels: Array[Pointer], d: Int, obsModels: Array[Pointer], p: Int, b: Int, t: Int,
+                       y: Array[Double], initMean: Array[Double], initCov: Array[Double], alpha: Double, beta: Double, kappa: Double,
+                       computeLl: Int, hiddenMeans: Array[Double], hiddenCovs: Array[Double], ll: Array[Double]): Int
   // ---- batched independent GPs (GPUnscentedKalmanFilter.scala:123-136, GPOptimizer.scala:54-61) ----
   def gpk_gp_nll_grad_batched(h: Pointer, b: Int, x: Array[Double], n: Int, d: Int, ldx: Long, strideX: Long, y: Array[Double],
                               thetas: Array[Double], hasSigmaNoise: Int, sigmaNoise: Double, nparams: Int, ll: Array[Double],
@@ -77,7 +81,7 @@ trait GpkLib extends Library {
   def gpk_ep_grad_from_factor(h: Pointer, x: Array[Double], n: Int, d: Int, ldx: Long, theta: Array[Double], k: Array[Double],
                               ldk: Long, tau: Array[Double], nu: Array[Double], l: Array[Double], ldl: Long, nparams: Int,
                               grad: Array[Double]): Int
-  // ---- one large GP on every GPU of the node (include/gpk_mg.h, libgpk_mg.so exports these next to libgpk's symbols) ----
+  // ---- one large GP on every GPU of the node (include/gpk.h "one large GP on all GPUs"; same libgpk.so) ----
   def gpk_mg_create(out: PointerByReference, ndev: Int, devices: Array[Int]): Int
   def gpk_mg_destroy(mg: Pointer): Int
   def gpk_mg_last_error(mg: Pointer): String
@@ -86,7 +90,6 @@ trait GpkLib extends Library {
 }
 
 object Gpk {
-  /** -Dgpk.lib=gpk_mg loads the multi-GPU build (a superset: it links libgpk's objects and adds gpk_mg_*). */
   val lib: GpkLib = Native.loadLibrary(System.getProperty("gpk.lib", "gpk"), classOf[GpkLib]).asInstanceOf[GpkLib]
 
   /** One handle per JVM, like the reference's Spring singletons (spring-context.xml:33-51).  A handle is not re-entrant:

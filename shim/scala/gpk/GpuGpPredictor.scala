@@ -141,4 +141,26 @@ object GpuFittedGp {
     check(lib.gpk_gp_models_mean_var(handle, models.map(_.token).toArray, models.length, xs.data, ms, ms, mean, variance))
     (new DenseMatrix(ms, models.length, mean).t, new DenseMatrix(ms, models.length, variance).t)
   }
+
+  /** dynamicalsystems/filtering/GPUnscentedKalmanFilter.inferHiddenState (GPUnscentedKalmanFilter.scala:26-34 over
+    * UnscentedKalmanFilter.scala:24-80) for B observation series in ONE device call: sysModels = one resident GP per state dimension
+    * (trained on z_t -> z_{t+1} - z_t, :105-113), obsModels = one per observation dimension (:115-121); observations(b) is
+    * p x T, priors (initMeans(b), initCovs(b)).  Returns per series (hiddenMeans d x T, hiddenCovs, logLikelihood). */
+  def filterMany(sysModels: Seq[GpuFittedGp], obsModels: Seq[GpuFittedGp], observations: Seq[DenseMatrix[Double]],
+                 initMeans: Seq[DenseVector[Double]], initCovs: Seq[DenseMatrix[Double]], alpha: Double = 1.0, beta: Double = 0.0,
+                 kappa: Double = 2.0): Seq[(DenseMatrix[Double], Array[DenseMatrix[Double]], Double)] = {
+    import Gpk.{check, handle, lib}
+    val (d, p, b, t) = (sysModels.length, obsModels.length, observations.length, observations.head.cols)
+    val y = observations.flatMap(_.copy.data).toArray                                  // p x T column-major per series
+    val m0 = initMeans.flatMap(_.toArray).toArray
+    val c0 = initCovs.flatMap(_.copy.data).toArray
+    val means = new Array[Double](b * t * d); val covs = new Array[Double](b * t * d * d); val ll = new Array[Double](b)
+    check(lib.gpk_gpukf_filter(handle, sysModels.map(_.token).toArray, d, obsModels.map(_.token).toArray, p, b, t, y, m0, c0,
+                               alpha, beta, kappa, 1, means, covs, ll))
+    (0 until b).map { s =>
+      val hm = new DenseMatrix(d, t, means.slice(s * t * d, (s + 1) * t * d))
+      val hc = Array.tabulate(t)(i => new DenseMatrix(d, d, covs.slice((s * t + i) * d * d, (s * t + i + 1) * d * d)))
+      (hm, hc, ll(s))
+    }
+  }
 }
