@@ -60,7 +60,8 @@ int pipe_min() {     // smallest padded N that takes the pipelined driver (0 dis
     return v;
 }
 
-int potrf_nb();
+int potrf_nb(int N);
+int potrf_nb_max();
 
 int batch_group_min() {   // smallest batch that is split into GPK_NGROUP concurrent groups (0 or less: never)
     static int v = -1;
@@ -193,7 +194,7 @@ static size_t rec_scratch_doubles(int N) {
 size_t gpk_chol_scratch_doubles(int N) {
     const size_t rec = rec_scratch_doubles(N);
     const size_t pipe = rec_scratch_doubles(pipe_nb()) + (size_t)pipe_nb() * N;   // diagonal-block scratch + one row panel
-    const size_t fact = rec_scratch_doubles(potrf_nb());
+    const size_t fact = rec_scratch_doubles(potrf_nb_max());
     const size_t m = rec > pipe ? rec : pipe;
     return m > fact ? m : fact;
 }
@@ -252,16 +253,21 @@ int col_update(gpk_handle h, double* A, const double* Li, int N, int bk, int sk,
 }  // namespace
 
 namespace {
-int potrf_nb() {     // block-column width of the factor-only driver (gpk_potrf_factor)
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("GPK_POTRF_NB"); v = e ? atoi(e) : 512; if (v < NB || v % NB) v = 512; }
-    return v;
+// block-column width of the factor-only driver.  Measured on B200 (profiles/r02_potrf_nb.log): n = 4096: 2.89 / 3.29 ms at
+// 256 / 512; n = 8192: 10.47 / 9.04 / 8.90 / 9.14 ms at 128 / 256 / 384 / 512; n = 16384: 52.3 / 49.0 ms at 256 / 512 -- the spine
+// (one diagonal block after the other) favours narrow blocks, the bulk GEMMs (K = width) wide ones.  GPK_POTRF_NB overrides.
+int potrf_nb(int N) {
+    static int forced = -2;
+    if (forced == -2) { const char* e = getenv("GPK_POTRF_NB"); forced = e ? atoi(e) : -1; if (forced > 0 && (forced < NB || forced % NB)) forced = -1; }
+    if (forced > 0) return forced;
+    return N <= 4096 ? 256 : (N <= 12288 ? 384 : 512);
 }
+int potrf_nb_max() { const int f = potrf_nb(1 << 30); return f > 512 ? f : 512; }
 }  // namespace
 
 int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, double* T, int N, int keep_L, int* info_dev,
                             cudaEvent_t* kinv_done, int factor_only, double* rhsB, double* rhsV, int rhsM) {
-    const int nbk = factor_only ? potrf_nb() : pipe_nb();
+    const int nbk = factor_only ? potrf_nb(N) : pipe_nb();
     const int nt = (N + nbk - 1) / nbk;
     auto bs = [&](int k) { return k * nbk < N ? k * nbk : N; };
     GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
@@ -464,7 +470,7 @@ int stage_panel(gpk_handle h, double* A, double* Li, int N, int bk, int sk, int 
 
 int potrf_factor_pipelined(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev, double* rhsB, double* rhsV,
                            int rhsM) {
-    const int nbk = potrf_nb();
+    const int nbk = potrf_nb(N);
     const int nt = (N + nbk - 1) / nbk;
     auto bs = [&](int k) { return k * nbk < N ? k * nbk : N; };
     GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
@@ -478,12 +484,15 @@ int potrf_factor_pipelined(gpk_handle h, double* A, double* Li, double* T, int N
     cudaEvent_t evUr_prev = nullptr;                 // S1 finished block column k (rows below block row k) of update k-1
     cudaEvent_t evG_next = nullptr;                  // S's column-first launch of step k-1: block column k+1 has updates <= k-1
     int rc;
+    Trace tr;
+    tr.start(M);
     for (int k = 0; k < nt; ++k) {
         const int bk = bs(k), sk = bs(k + 1) - bk;
         rc = potrf_inv_rec(c, A + bk + (int64_t)bk * N, Li + bk + (int64_t)bk * N, T, sk, bk, 0);                   // F_k
         if (rc) return rc;
         cudaEvent_t evF = next_event(h);
         GPK_CUDA(h, cudaEventRecord(evF, M));
+        tr.mark(M, "M:F", k);
         cudaEvent_t evPc = nullptr, evPr = nullptr, evG_this = nullptr;
         if (k + 1 < nt) {
             const int b1 = bs(k + 1), b2 = bs(k + 2), s1 = b2 - b1;
@@ -493,8 +502,10 @@ int potrf_factor_pipelined(gpk_handle h, double* A, double* Li, double* T, int N
             evPc = next_event(h);
             GPK_CUDA(h, cudaEventRecord(evPc, M));
             if (evG_next) GPK_CUDA(h, cudaStreamWaitEvent(M, evG_next, 0));
+            tr.mark(M, "M:Pc", k);
             rc = stage_update(h, A, Li, N, bk, sk, b1, s1, b1, s1, 1);                                               // Uc_k
             if (rc) return rc;
+            tr.mark(M, "M:Uc", k);
             evUr_prev = nullptr;
             if (k + 2 < nt) {
                 {
@@ -510,6 +521,7 @@ int potrf_factor_pipelined(gpk_handle h, double* A, double* Li, double* T, int N
                     if (rc) return rc;
                     evUr_prev = next_event(h);
                     GPK_CUDA(h, cudaEventRecord(evUr_prev, S1));
+                    tr.mark(S1, "S1:Ur", k);
                 }
                 {
                     GPK_CUDA(h, cudaStreamWaitEvent(S, evPc, 0));
@@ -520,10 +532,12 @@ int potrf_factor_pipelined(gpk_handle h, double* A, double* Li, double* T, int N
                     if (rc) return rc;
                     evG_this = next_event(h);
                     GPK_CUDA(h, cudaEventRecord(evG_this, S));
+                    tr.mark(S, "S:G", k);
                     if (k + 3 < nt) {
                         rc = col_update(h, A, Li, N, bk, sk, b3, N - b3);                                            // U_k(k+3:, k+3:)
                         if (rc) return rc;
                     }
+                    tr.mark(S, "S:bulk", k);
                 }
             }
             evG_next = evG_this;
@@ -562,6 +576,7 @@ int potrf_factor_pipelined(gpk_handle h, double* A, double* Li, double* T, int N
         GPK_CUDA(h, cudaEventRecord(e3, R));
         GPK_CUDA(h, cudaStreamWaitEvent(M, e3, 0));
     }
+    tr.dump();
     return GPK_OK;
 }
 
@@ -571,7 +586,7 @@ int potrf_factor_pipelined(gpk_handle h, double* A, double* Li, double* T, int N
 // look-ahead driver without the inverse rows and the K^-1 accumulation -- n^3/3 flops instead of n^3.  Only the diagonal
 // blocks are inverted (the panels are solved as GEMMs with them).  Li is still an N x N staging area.
 int gpk_potrf_factor(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev) {
-    if (N >= 2 * potrf_nb()) return potrf_factor_pipelined(h, A, Li, T, N, info_dev, nullptr, nullptr, 0);
+    if (N >= 2 * potrf_nb(N)) return potrf_factor_pipelined(h, A, Li, T, N, info_dev, nullptr, nullptr, 0);
     return gpk_potrf_inv(h, A, Li, T, N, 1, info_dev, 1);
 }
 
@@ -580,7 +595,7 @@ int gpk_potrf_factor(gpk_handle h, double* A, double* Li, double* T, int N, int*
 // sides) is this call.  Large N: the look-ahead driver with the right-hand sides riding along (no L^-1 is ever formed:
 // n^3/3 + n^2 M flops); small N: L^-1 by the recursion and one GEMM.
 int gpk_potrf_factor_solve(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev, double* B, double* V, int M) {
-    if (N >= 2 * potrf_nb())
+    if (N >= 2 * potrf_nb(N))
         return potrf_factor_pipelined(h, A, Li, T, N, info_dev, B, V, M);
     int rc = gpk_potrf_inv(h, A, Li, T, N, 1, info_dev, 1);
     if (rc) return rc;

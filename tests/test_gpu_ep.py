@@ -123,9 +123,11 @@ def test_ep_requirements():
         gp.EpParameterEstimator(np.eye(4), np.ones(4, dtype=np.int32), lambda ctx: True).estimateSiteParams
 
 
-def test_c3_config_full_size_properties():
-    """BASELINE.json config 3 at full size (n = 4096, D = 4): the CPU oracle needs minutes per sweep here, so the check is
-    through size-independent properties of a finished EP run."""
+def test_c3_config_full_size_parity_and_properties():
+    """BASELINE.json config 3 at full size (n = 4096, D = 4).  Parity: the committed golden tests/golden/c3_full.npz holds three
+    fixed sweeps of the LAPACK-backed oracle on exactly this input (generated once in the build container by
+    tests/golden/make_golden.py c3_full -- the CPU oracle needs minutes per sweep); tau, nu, mu, the cavity parameters, diag L and
+    log Z must agree to 1e-9.  Then the size-independent properties of a finished EP run."""
     X, t, th = orc.make_c3()
     n = X.shape[0]
     kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(th[0], th[1:-1], th[-1]))
@@ -134,6 +136,13 @@ def test_c3_config_full_size_properties():
     site, L = est.estimateSiteParams
     tau, nu = site.tauSiteParams, site.niSiteParams
     assert est.sweeps == 3 and np.all(np.isfinite(tau)) and np.all(tau > 0) and np.all(np.isfinite(nu))
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c3_full.npz"))
+    assert int(gold["n"]) == n and int(gold["sweeps"]) == 3
+    assert float(gold["x_checksum"]) == float(X.sum()) and int(gold["t_checksum"]) == int(t.sum())   # same seeded input
+    for name, got in (("tau", tau), ("nu", nu), ("mu", est.mu), ("diagL", np.diag(L))):
+        want = gold[name]
+        assert np.all(np.abs(got - want) <= 1e-9 * np.maximum(np.abs(want), 1e-3 * np.abs(want).max())), name
+    assert abs(site.marginalLogLikelihood - float(gold["logZ"])) <= 1e-9 * abs(float(gold["logZ"]))
     st = np.sqrt(tau)
     Bm = np.eye(n) + (st[:, None] * st[None, :]) * K                          # EpParameterEstimator.scala:58
     assert np.linalg.norm(L @ L.T - Bm) <= 8 * n * np.finfo(float).eps * np.linalg.norm(Bm)
