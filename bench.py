@@ -300,7 +300,7 @@ def bench_c4(h, dist, rank, world, reps=5):
     return rec
 
 
-def bench_c5(dist, rank, world, local, cpu_group=None, n=65536, nb=1024, reps=2):
+def bench_c5(dist, rank, world, local, cpu_group=None, n=65536, nb=None, reps=2):
     """One GP of n = 65536, D = 8 (seed 5): K build + 2-D block-cyclic FP64 Cholesky + both solves + log-likelihood
     (GpPredictor.scala:104-124,144-149) through DistributedGp.fit.  Strong scaling.  CUDA events per rank, max over ranks."""
     import numpy as np
@@ -309,6 +309,8 @@ def bench_c5(dist, rank, world, local, cpu_group=None, n=65536, nb=1024, reps=2)
     from gp_algos_b200.distributed import DistributedGp, choose_grid
     X, y, theta = synthetic.make_c2(n=n, D=DIM, seed=5)
     grid = choose_grid(world)
+    if nb is None:
+        nb = 512 if world >= 8 else 1024      # narrower blocks shorten the serial factor -> panel -> broadcast chain (0.438 vs 0.450 s on 8)
     solver = DistributedGp(grid=grid, nb=nb, device=local)
     times, fit = [], None
     for _ in range(reps):
@@ -328,11 +330,11 @@ def bench_c5(dist, rank, world, local, cpu_group=None, n=65536, nb=1024, reps=2)
     # peer-to-peer panel puts; rank 0 runs it while the other ranks wait on a CPU (gloo) barrier, their GPUs idle
     try:
         cabi = {"what": "gpk_mg_potrf_solve: single process, round-robin block columns, cudaMemcpy2DAsync peer puts (no NCCL)",
-                "ndev": world, "nb": nb}
+                "ndev": world, "nb": "automatic (gpk_mg_set_block(0): 1024 up to 4 devices, 512 on 8 at this n)"}
         alpha_c = torch.zeros(n, dtype=torch.float64, device="cuda")
         if rank == 0:
             from gp_algos_b200.multi_gpu import MultiGpuGp
-            mg = MultiGpuGp(world, nb=nb)
+            mg = MultiGpuGp(world)                  # block width: the library's automatic choice
             runs = [mg.fit(X, y, theta) for _ in range(reps)]
             mg.close()
             f = min(runs, key=lambda r: r.seconds)

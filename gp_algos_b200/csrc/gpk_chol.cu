@@ -609,24 +609,40 @@ int gpk_potrf_factor_solve(gpk_handle h, double* A, double* Li, double* T, int N
 bool gpk_use_pipelined(int N, int batch) { return batch == 1 && pipe_min() > 0 && N >= pipe_min() && N >= 2 * pipe_nb(); }
 
 int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int* info_dev, int batch) {
-    if (gpk_use_pipelined(N, batch)) return gpk_potrf_inv_pipelined(h, A, Li, nullptr, T, N, keep_L, info_dev, nullptr);
+    return gpk_potrf_inv_grouped(h, A, Li, T, N, keep_L, info_dev, batch, nullptr);
+}
+
+// `post(b0, cnt)` (may be empty) is called once per batch group, right behind the group's factorisation and on the group's
+// stream (h->stream is swapped for the call): what it enqueues for problems [b0, b0 + cnt) -- alpha, log-likelihood, K^-1,
+// gradient trace -- overlaps the OTHER group's latency-bound spine instead of waiting for every group to finish.
+int gpk_potrf_inv_grouped(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int* info_dev, int batch,
+                          const std::function<int(int, int)>& post) {
+    if (gpk_use_pipelined(N, batch)) {
+        int rc = gpk_potrf_inv_pipelined(h, A, Li, nullptr, T, N, keep_L, info_dev, nullptr);
+        return (rc || !post) ? rc : post(0, batch);
+    }
     GPK_CUDA(h, cudaMemsetAsync(info_dev, 0, sizeof(int) * (size_t)batch, h->stream));
     const int64_t sM = (int64_t)N * N, sT = (int64_t)gpk_chol_scratch_doubles(N);
     const int groups = batch_groups(batch);
     if (groups == 1) {
         Ctx c{h, N, N, keep_L, info_dev, batch, sM, sT, 0};
-        return potrf_inv_rec(c, A, Li, T, N, 0, 0);
+        int rc = potrf_inv_rec(c, A, Li, T, N, 0, 0);
+        return (rc || !post) ? rc : post(0, batch);
     }
     // Batch groups: the problems are independent, so the batch is cut in two halves that walk the recursion on two streams.
     // The base-case launches (one CTA per problem, latency-bound, ~40 us each, 8 per factorisation at n = 1024) and the
     // partial last waves of the small GEMMs of one half are filled by the other half's launches.
     cudaEvent_t ev0 = next_event(h);
     GPK_CUDA(h, cudaEventRecord(ev0, h->stream));
-    const int per = (batch + groups - 1) / groups;
+    // the group on the side stream is enqueued first and gets the smaller share (GPK_GROUP_SPLIT = share of the handle's own
+    // stream, default 0.5): its post stage then starts while the other group is still in its spine
+    static double split = -1.0;
+    if (split < 0) { const char* e = getenv("GPK_GROUP_SPLIT"); split = e ? atof(e) : 0.5; if (!(split > 0.1 && split < 0.9)) split = 0.5; }
+    const int per = groups == 2 ? (int)(batch * split + 0.5) : (batch + groups - 1) / groups;
     int rc = GPK_OK;
     cudaEvent_t done[GPK_NGROUP];
     for (int g = groups - 1; g >= 0 && !rc; --g) {       // the handle's own stream last: its launches need no join
-        const int b0 = g * per, cnt = (batch - b0 < per) ? batch - b0 : per;
+        const int b0 = g * per, cnt = (groups == 2 && g == 1) ? batch - per : ((batch - b0 < per) ? batch - b0 : per);
         done[g] = nullptr;
         if (cnt <= 0) continue;
         cudaStream_t st = g == 0 ? h->stream : h->grp[g - 1];
@@ -635,6 +651,7 @@ int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int kee
             StreamSwap sw(h, st);
             Ctx c{h, N, N, keep_L, info_dev + b0, cnt, sM, sT, 4 * g};
             rc = potrf_inv_rec(c, A + b0 * sM, Li + b0 * sM, T + b0 * sT, N, 0, 0);
+            if (!rc && post) rc = post(b0, cnt);
         }
         if (g > 0 && !rc) {
             done[g] = next_event(h);

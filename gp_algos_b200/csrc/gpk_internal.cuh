@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <functional>
+
 #include "../../include/gpk.h"
 
 #define GPK_TILE 128
@@ -227,6 +229,9 @@ int gpk_base_potrf_trtri(gpk_handle h, double* A, int64_t lda, double* Li, int64
                          int batch, int64_t strideA, int64_t strideLi, int info_stride, int coloff_stride);
 size_t gpk_chol_scratch_doubles(int N);
 int gpk_potrf_inv(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int* info_dev, int batch = 1);
+// same, with a per-batch-group continuation: post(b0, cnt) is enqueued on the group's stream right behind its factorisation
+int gpk_potrf_inv_grouped(gpk_handle h, double* A, double* Li, double* T, int N, int keep_L, int* info_dev, int batch,
+                          const std::function<int(int, int)>& post);
 // Look-ahead driver for one large problem (see gpk_chol.cu): same results as gpk_potrf_inv; when Kinv != nullptr it also
 // accumulates K^-1 = Li^t Li (lower tiles) into Kinv (N x N, ld N, a buffer distinct from A and Li).
 bool gpk_use_pipelined(int N, int batch);

@@ -33,13 +33,14 @@ namespace {
 constexpr int MG_MAXDEV = 16;
 constexpr int MG_NLANE = 2;
 constexpr int MG_NSLOT = 3;
+constexpr int MG_NCOPY = 3;           // put streams per device: the next owner gets its own, the other peers alternate on the rest
 
 struct MgDev {
     int dev;
     gpk_handle h;                    // main (high-priority) stream
     gpk_handle lane[MG_NLANE];       // low-priority bulk lanes
     cudaStream_t lane_stream[MG_NLANE];
-    cudaStream_t copy;               // outgoing puts
+    cudaStream_t copy[MG_NCOPY];     // outgoing puts
     double* buf;                     // one allocation, carved below
     size_t buf_bytes;
     double *A, *panel[MG_NSLOT], *Dbuf, *LiAll, *X, *y0, *ypad, *z, *alpha, *tmp, *scal;
@@ -148,7 +149,7 @@ int gpk_mg_create(gpk_mg* out, int ndev, const int* devices) {
     if (!mg) return GPK_ENOMEM;
     memset(mg, 0, sizeof(*mg));
     mg->G = ndev;
-    mg->nb = 1024;
+    mg->nb = 0;      // automatic
     for (int g = 0; g < ndev; ++g) {
         MgDev& dv = mg->d[g];
         dv.dev = devices ? devices[g] : g;
@@ -164,7 +165,8 @@ int gpk_mg_create(gpk_mg* out, int ndev, const int* devices) {
             gpk_set_graph_mode(dv.lane[l], 0);
         }
         gpk_set_graph_mode(dv.h, 0);
-        if (cudaStreamCreateWithPriority(&dv.copy, cudaStreamNonBlocking, greatest) != cudaSuccess) { gpk_mg_destroy(mg); return GPK_ECUDA; }
+        for (int c = 0; c < MG_NCOPY; ++c)
+            if (cudaStreamCreateWithPriority(&dv.copy[c], cudaStreamNonBlocking, greatest) != cudaSuccess) { gpk_mg_destroy(mg); return GPK_ECUDA; }
     }
     // peer mappings for the puts (NVLink / NVSwitch on a B200 node); without them cudaMemcpy2DAsync stages through the host
     for (int g = 0; g < ndev; ++g) {
@@ -191,7 +193,8 @@ int gpk_mg_destroy(gpk_mg mg) {
             if (dv.lane_stream[l]) cudaStreamDestroy(dv.lane_stream[l]);
         }
         if (dv.h) gpk_destroy(dv.h);
-        if (dv.copy) cudaStreamDestroy(dv.copy);
+        for (int c = 0; c < MG_NCOPY; ++c)
+            if (dv.copy[c]) cudaStreamDestroy(dv.copy[c]);
         if (dv.buf) cudaFree(dv.buf);
     }
     delete mg;
@@ -203,7 +206,8 @@ int gpk_mg_device_count(gpk_mg mg) { return mg ? mg->G : 0; }
 double gpk_mg_last_seconds(gpk_mg mg) { return mg ? mg->last_seconds : 0.0; }
 int64_t gpk_mg_last_put_bytes(gpk_mg mg) { return mg ? mg->put_bytes : 0; }
 int gpk_mg_set_block(gpk_mg mg, int nb) {
-    if (!mg || nb < GPK_TILE || nb % GPK_TILE) return mg_error(mg, GPK_EINVAL, "block width must be a positive multiple of 128%s", nullptr);
+    if (!mg || nb < 0 || (nb > 0 && (nb < GPK_TILE || nb % GPK_TILE)))
+        return mg_error(mg, GPK_EINVAL, "block width must be 0 (automatic) or a positive multiple of 128%s", nullptr);
     mg->nb = nb;
     return GPK_OK;
 }
@@ -212,7 +216,14 @@ int gpk_mg_potrf_solve(gpk_mg mg, const double* X, int n, int D, int64_t ldx, co
                        int has_s, double s, double* alpha_out, double* ll_out, int* info_out) {
     if (!mg || !X || !y || !theta || n <= 0 || ldx < n) return mg_error(mg, GPK_EINVAL, "gpk_mg_potrf_solve: bad arguments%s", nullptr);
     if (D < 1 || D > GPK_MAX_D) return mg_error(mg, GPK_EINVAL, "gpk_mg_potrf_solve: feature dimension outside 1..64%s", nullptr);
-    const int G = mg->G, nb = mg->nb;
+    const int G = mg->G;
+    // automatic block width: at least ~16 block columns per device (the serial chain factor -> panel -> put shrinks with the
+    // width, the bulk GEMMs want it large): 1024 up to 4 devices at n = 65536, 512 on 8 (measured 0.431 vs 0.417 s)
+    int nb = mg->nb;
+    if (nb <= 0) {
+        nb = (n / (16 * G)) / GPK_TILE * GPK_TILE;
+        nb = nb < 256 ? 256 : (nb > 1024 ? 1024 : nb);
+    }
     const int nt = (n + nb - 1) / nb, N = nt * nb;
     const double sn2 = theta[D + 1] * theta[D + 1] + (has_s ? s : 0.0);          // KernelRequisites.scala:69 + GpPredictor.scala:116
     mg->err[0] = 0; mg->last_info = 0; mg->put_bytes = 0;
@@ -269,7 +280,7 @@ int gpk_mg_potrf_solve(gpk_mg mg, const double* X, int n, int D, int64_t ldx, co
             cudaEvent_t built = pool.get(mg, g);
             MG_CUDA(mg, cudaEventRecord(built, dv.h->stream));
             for (int l = 0; l < MG_NLANE; ++l) MG_CUDA(mg, cudaStreamWaitEvent(dv.lane_stream[l], built, 0));
-            MG_CUDA(mg, cudaStreamWaitEvent(dv.copy, built, 0));
+            for (int c = 0; c < MG_NCOPY; ++c) MG_CUDA(mg, cudaStreamWaitEvent(dv.copy[c], built, 0));
         }
         // events: arr[g][k] panel k is in device g's buffer; used[g][k][0..NLANE] device g no longer reads panel k
         std::vector<std::vector<cudaEvent_t>> arr(G, std::vector<cudaEvent_t>(nt, nullptr));
@@ -298,13 +309,14 @@ int gpk_mg_potrf_solve(gpk_mg mg, const double* X, int n, int D, int64_t ldx, co
             arr[o][k] = pool.get(mg, o);
             MG_CUDA(mg, cudaEventRecord(arr[o][k], M));
             if (G > 1) {
-                MG_CUDA(mg, cudaStreamWaitEvent(dv.copy, arr[o][k], 0));
-                for (int q = 1; q < G; ++q) {                                                 // next owner first
+                for (int c = 0; c < MG_NCOPY; ++c) MG_CUDA(mg, cudaStreamWaitEvent(dv.copy[c], arr[o][k], 0));
+                for (int q = 1; q < G; ++q) {                                                 // next owner first, on its own stream
                     const int g = (o + q) % G;
-                    if (k >= MG_NSLOT) for (cudaEvent_t e : used[g][k - MG_NSLOT]) MG_CUDA(mg, cudaStreamWaitEvent(dv.copy, e, 0));
-                    MG_CUDA(mg, copy_block(mg->d[g].panel[slot] + bk, N, pan + bk, N, N - bk, nb, dv.copy));
+                    cudaStream_t cs = dv.copy[q == 1 ? 0 : 1 + (q % (MG_NCOPY - 1))];
+                    if (k >= MG_NSLOT) for (cudaEvent_t e : used[g][k - MG_NSLOT]) MG_CUDA(mg, cudaStreamWaitEvent(cs, e, 0));
+                    MG_CUDA(mg, copy_block(mg->d[g].panel[slot] + bk, N, pan + bk, N, N - bk, nb, cs));
                     arr[g][k] = pool.get(mg, o);
-                    MG_CUDA(mg, cudaEventRecord(arr[g][k], dv.copy));
+                    MG_CUDA(mg, cudaEventRecord(arr[g][k], cs));
                     mg->put_bytes += (int64_t)(N - bk) * nb * 8;
                 }
             }

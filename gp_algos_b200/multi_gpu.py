@@ -23,7 +23,7 @@ class MultiGpuFit(NamedTuple):
 
 
 class MultiGpuGp:
-    def __init__(self, ndev: int = 0, devices: Optional[Sequence[int]] = None, nb: int = 1024):
+    def __init__(self, ndev: int = 0, devices: Optional[Sequence[int]] = None, nb: int = 0):
         self.lib = _lib.load()
         self._mg = C.c_void_p()
         dev = None

@@ -257,7 +257,7 @@ int gpk_sum_log_diag_dev(gpk_handle h, const double* dA, int64_t ld, int n, doub
  * (cudaDeviceEnablePeerAccess: NVLink / NVSwitch on a B200 node).  gpk_mg_potrf_solve is GpPredictor.preComputeComponents +
  * logLikelihood (GpPredictor.scala:104-124,144-149) for one training set: K is built block column by block column on the
  * owning device from the replicated X (never communicated), factored right-looking with look-ahead 1 on a round-robin block-
- * column layout (width gpk_mg_set_block, default 1024), each step's panel PUT into every peer's buffer by cudaMemcpy2DAsync over
+ * column layout (width gpk_mg_set_block; default 0 = automatic, 256..1024 by n and the device count), each step's panel PUT into every peer's buffer by cudaMemcpy2DAsync over
  * the peer mapping (no collective, event-ordered), alpha by a forward solve that rides along and a back solve over the owners.
  * Outputs: alpha[n], ll, *info = 0 or the failing leading minor (GPK_ENOTPD).  Results on 1, 2, 4, 8 devices agree to rounding
  * (the summation order of the trailing updates does not depend on the device count).
