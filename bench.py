@@ -26,6 +26,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# more hardware work queues than the default 8: libgpk's drivers use up to ~20 streams per handle (see gp_algos_b200/__init__.py);
+# must be in the environment before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 N_TRAIN, DIM = 8192, 8
 NPARAMS = DIM + 2

@@ -17,7 +17,15 @@ and error behaviour), used by the parity tests and the benchmark:
 There is no CPU fallback: importing works anywhere, but every numeric call raises if libgpk.so or a
 CUDA device is missing.
 """
-from .kernel_requisites import GaussianRbfKernel, GaussianRbfParams  # noqa: F401
+import os as _os
+
+# libgpk runs its look-ahead drivers and batch groups on up to ~20 CUDA streams per handle; with the default of 8 hardware work
+# queues several streams share a queue and serialise falsely (measured: 3 / 4 batch groups 3.73 / 3.70 ms -> 3.38 ms for 64 problems
+# of n = 1024, profiles/r02_c4_maxconn.log).  The variable is read when the CUDA context is created, so it is set at import time
+# unless the host application already chose a value.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from .kernel_requisites import GaussianRbfKernel, GaussianRbfParams  # noqa: F401,E402
 from .co2_prediction import Co2HyperParams, Co2Kernel, co2DataToYearWithValue  # noqa: F401
 from .gp_predictor import GpPredictor, PredictionInput, PredictionTrainingInput, GaussianDistribution  # noqa: F401
 from . import matrix_utils as MatrixUtils  # noqa: F401

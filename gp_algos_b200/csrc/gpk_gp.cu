@@ -130,33 +130,6 @@ int nll_grad_core(gpk_handle h, int B, const double* dX, int n, int D, int64_t l
             Kinv = (double*)gpk_arena(h, ARENA_KINV, (size_t)w.N * w.N * sizeof(double));
             if (!Kinv) return GPK_ENOMEM;
         }
-        if (bc > 1 && !Kinv) {
-            // batched problems: every batch group of the factorisation carries its own post stage (alpha, log-likelihood, K^-1,
-            // gradient trace) on its stream, so one group's large K^-1 GEMM fills the GPU under the other group's spine
-            rc = gpk_cov_sym_lower_padded(h, X, n, ldx, pp0.cp, w.A, w.N, bc, strideX, w.pp_dev);
-            if (rc) return rc;
-            const int N = w.N;
-            const int64_t sM = (int64_t)N * N;
-            const double* dyb = dy + (size_t)b0 * n;
-            double* outb = out_dev + b0 * so;
-            auto post = [&](int g0, int cnt) -> int {
-                int r = gpk_pad_vector(h, w.ypad + (size_t)g0 * N, N, dyb + (size_t)g0 * n, n, cnt);
-                if (r) return r;
-                r = gpk_trmv_lower(h, w.Li + g0 * sM, N, w.ypad + (size_t)g0 * N, w.z + (size_t)g0 * N, w.scratch + (size_t)g0 * w.sScratch, cnt);
-                if (r) return r;
-                r = gpk_trmv_lower_t(h, w.Li + g0 * sM, N, w.z + (size_t)g0 * N, w.alpha + (size_t)g0 * N, cnt);
-                if (r) return r;
-                r = gpk_loglik(h, w.A + g0 * sM, N, n, w.ypad + (size_t)g0 * N, w.alpha + (size_t)g0 * N, outb + g0 * so, cnt, so);
-                if (r || nparams <= 0) return r;
-                r = gpk_lauum_lower(h, w.Li + g0 * sM, w.A + g0 * sM, N, cnt);
-                if (r) return r;
-                return gpk_grad_trace(h, w.A + g0 * sM, N, X + g0 * strideX, n, ldx, w.alpha + (size_t)g0 * N, pp0, nparams, outb + g0 * so + 1,
-                                      w.scratch + (size_t)g0 * w.sScratch, cnt, strideX, w.pp_dev + g0, so);
-            };
-            rc = gpk_potrf_inv_grouped(h, w.A, w.Li, w.T, N, 0, info, bc, post);
-            if (rc) return rc;
-            continue;
-        }
         cudaEvent_t kinv_done = nullptr;
         rc = fit_core(h, w, bc, X, n, D, ldx, strideX, dy + (size_t)b0 * n, pp0, 0, w.Li, w.alpha, out_dev + b0 * so, so, info, Kinv,
                       &kinv_done, on_dev);

@@ -51,6 +51,10 @@ int gpk_synchronize(gpk_handle h);
 /* number of kernel launches issued through this handle since creation (bench.py "gpu_launches") */
 int64_t gpk_launch_count(gpk_handle h);
 const char* gpk_version(void);
+/* Development aid, not part of the drop-in surface: runs the 128 x 128 diagonal-block kernel (factor + triangular inverse, the
+ * serial spine of every factorisation) once on a synthetic SPD block and returns 17 clock64() stamps, one per phase
+ * (tools/base_timing.py prints them; profiles/r02_base_timing.log). */
+int gpk_debug_base_timing(gpk_handle h, long long* stamps_host);
 /* Launch sequences that callers repeat verbatim are captured into CUDA graphs and replayed: the single-problem
  * gpk_gp_nll_grad[_dev] evaluation (an optimiser's objective, GpPredictor.scala:126-142; same buffers and shape, new
  * hyper-parameters through device memory) from its second call on, and the EP sweep (EpParameterEstimator.scala:37-67) once
@@ -132,6 +136,14 @@ int gpk_syrk_lower_dev(gpk_handle h, const double* dP, int64_t ldp, double* dC, 
 int gpk_gp_fit(gpk_handle h, const double* X, int n, int D, int64_t ldx, const double* y,
                const double* theta, int has_sigma_noise, double sigma_noise, double* L, int64_t ldl,
                double* alpha, double* ll);
+/* Numerics of the fused pipelines (gpk_gp_fit, gpk_gp_nll_grad, gpk_gp_model_*, the batched calls): the factorisation builds
+ * L^-1 alongside L (blocked, DMMA), and alpha = L^-t (L^-1 y), V = L^-1 K*^t, K^-1 = L^-t L^-1 are PRODUCTS with that explicit
+ * inverse, not substitutions.  Forward error of alpha is therefore bounded by O(n eps cond(L)^2) = O(n eps cond(K)) -- the same
+ * order as substitution's bound for the SOLUTION, but without substitution's small-residual guarantee: ||K alpha - y|| / ||y|| is
+ * O(n eps cond(K)) rather than O(n eps).  Measured: 2e-12 at n = 65536 (cond ~ 2e6), parity with the reference's row-oriented
+ * substitution 1e-9 relative on the BASELINE configs and 1e-7 on the Boston set (cond(K) = 1e8), which is the stated
+ * tolerance scaling 1e-9 max(1, cond / 1e5) of the tests.  Callers that need dtrsv-grade residuals use gpk_trsm (blocked
+ * substitution on 128-block inverses) on the returned L. */
 /* gp/regression/GpPredictor.scala:60-80 logLikelihoodWithDerivatives: ll and g[nparams],
  * g_p = 1/2 tr((alpha alpha^t - K^-1) dK/dtheta_{p+1}).  K, L, L^-1, K^-1 never leave the device
  * and dK/dtheta is never materialised. */

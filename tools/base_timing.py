@@ -3,7 +3,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gp_algos_b200 import _lib
 h = _lib.default_handle()
 st = (C.c_longlong * 17)()
-h.lib.gpk_debug_base_timing.argtypes = [C.c_void_p, C.c_void_p]
 for rep in range(2):
     h.check(h.lib.gpk_debug_base_timing(h.h, C.addressof(st)))
     v = list(st)
