@@ -110,7 +110,8 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     v = 1.0 / dt
     sample = (f"each step = one full n={n} evaluation through the oracle's LAPACK-backed port (OpenBLAS dpotrf+dpotri, "
-              f"fused O(n^2 P) gradient, {cores} threads); the Scala reference as written does ~23x more flops single-threaded")
+              f"fused O(n^2 P) gradient on a {cores}-thread pool, {cores} BLAS threads); the Scala reference as written does ~23x more flops "
+              f"single-threaded")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -558,7 +559,8 @@ def run_gpk(args):
             t_cpu = cpu_eval_time(n)
             t_lit = cpu_literal_time(768)
             cpu = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"one full n={n} evaluation, oracle LAPACK-backed port (OpenBLAS, {cores} threads): {t_cpu:.2f} s",
+                   "sample": f"one full n={n} evaluation, oracle LAPACK-backed port (OpenBLAS dpotrf + dpotri with {cores} threads, fused "
+                             f"gradient on a {cores}-thread pool): {t_cpu:.2f} s",
                    "literal_port_n768_s": t_lit,
                    "literal_port_extrapolated_n8192_s": t_lit * (8192 / 768) ** 3,
                    "literal_note": "line-by-line C restatement of the Scala path, 1 thread, timed at n=768 and scaled by n^3"}

@@ -485,27 +485,42 @@ def fast_loglik_with_derivs(X, y, theta, sigma_noise=None, nparams=None, block=1
     ll = fast_loglik(alpha, L, y)
     Kinv, info = sla.lapack.dpotri(L, lower=1)
     assert info == 0
-    # dpotri fills the lower triangle only; symmetrise by blocks while accumulating.
+    # dpotri fills the lower triangle only; symmetrise by blocks while accumulating.  The block pairs are independent: they
+    # run on a thread pool (NumPy releases the GIL inside its ufuncs) so that the timed CPU baseline uses every host core in
+    # this leg too, and their partial gradients are added in block order (deterministic).
+    pairs = [(i0, j0) for i0 in range(0, n, block) for j0 in range(0, min(n, i0 + block), block)]
+
+    def one(pair):
+        i0, j0 = pair
+        i1, j1 = min(n, i0 + block), min(n, j0 + block)
+        gb = np.zeros(D + 2)
+        Wb = np.outer(alpha[i0:i1], alpha[j0:j1]) - Kinv[i0:i1, j0:j1]
+        if i0 == j0:
+            Wl = np.tril(Wb, -1)
+            Wb = Wl + Wl.T + np.diag(np.diag(Wb))
+            mult = 1.0
+        else:
+            mult = 2.0
+        E = np.exp(-0.5 * _scaled_sqdist(X[i0:i1], X[j0:j1], ls))
+        WE = Wb * E
+        gb[0] = mult * (2 * sf) * WE.sum()
+        for d in range(D):
+            diff = X[i0:i1, d][:, None] - X[j0:j1, d][None, :]
+            gb[1 + d] = mult * (sf * sf) * float((WE * (diff * diff)).sum()) * ls[d] ** -3
+        if i0 == j0:
+            gb[D + 1] = (2 * sn) * float(np.trace(Wb))
+        return gb
+
+    workers = min(len(pairs), os.cpu_count() or 1)
+    if workers > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            parts = list(ex.map(one, pairs))
+    else:
+        parts = [one(pq) for pq in pairs]
     g = np.zeros(D + 2)
-    for i0 in range(0, n, block):
-        i1 = min(n, i0 + block)
-        for j0 in range(0, i1, block):
-            j1 = min(n, j0 + block)
-            Wb = np.outer(alpha[i0:i1], alpha[j0:j1]) - Kinv[i0:i1, j0:j1]
-            if i0 == j0:
-                Wl = np.tril(Wb, -1)
-                Wb = Wl + Wl.T + np.diag(np.diag(Wb))
-                mult = 1.0
-            else:
-                mult = 2.0
-            E = np.exp(-0.5 * _scaled_sqdist(X[i0:i1], X[j0:j1], ls))
-            WE = Wb * E
-            g[0] += mult * (2 * sf) * WE.sum()
-            for d in range(D):
-                diff = X[i0:i1, d][:, None] - X[j0:j1, d][None, :]
-                g[1 + d] += mult * (sf * sf) * float((WE * (diff * diff)).sum()) * ls[d] ** -3
-            if i0 == j0:
-                g[D + 1] += (2 * sn) * float(np.trace(Wb))
+    for gb in parts:
+        g += gb
     return ll, 0.5 * g[:nparams]
 
 
