@@ -65,3 +65,29 @@ def test_sharded_map_world_size_2(B):
 def test_sharded_map_without_process_group_runs_everything_locally():
     a, = sharded_map(6, lambda lo, hi: (np.arange(lo, hi),))
     assert np.array_equal(a, np.arange(6))
+
+
+def test_stack_problems_takes_a_breeze_layout_stack_without_copying():
+    """A (B, n, D) view over a (B, D, n) C-order block IS a stack of column-major n x D matrices (Breeze layout): the batched
+    entry points must hand it to the C ABI as it is (bench.py's end-to-end leg passes pinned memory this way)."""
+    from gp_algos_b200.batched import _stack_problems
+    base = np.arange(4 * 3 * 5, dtype=np.float64).reshape(4, 3, 5)          # (B, D, n)
+    X = base.transpose(0, 2, 1)                                              # (B, n, D) view
+    buf, strideX, n, D = _stack_problems(X, 4)
+    assert (strideX, n, D) == (15, 5, 3) and np.shares_memory(buf, base) and buf.flags.c_contiguous
+    Xc = np.ascontiguousarray(X)                                             # ordinary C-order stack: one transposing copy
+    buf2, _, _, _ = _stack_problems(Xc, 4)
+    assert np.array_equal(buf2, base) and not np.shares_memory(buf2, Xc)
+    shared, s0, _, _ = _stack_problems(Xc[0], 4)                             # one shared (n, D) matrix: stride 0
+    assert s0 == 0 and shared.flags.f_contiguous
+
+
+def test_gp_ukf_host_side_requirements_without_a_device():
+    import gp_algos_b200 as gp
+    kf = gp.GaussianRbfKernel(gp.GaussianRbfParams(1.0, [1.0, 1.0], 0.1))
+    ukf = gp.GPUnscentedKalmanFilter(None, gp.GpPredictor(kf))
+    with pytest.raises(ValueError):                                          # require: the GP state-space model is learned first
+        ukf.filter_many([np.zeros((2, 5))], [np.zeros(2)], [np.eye(2)])
+    p = gp.UnscentedTransformParams()
+    assert (p.alpha, p.beta, p.kappa) == (1.0, 0.0, 2.0)                     # UnscentedKalmanFilter.scala:186 defaults
+    assert gp.UnscentedTransformParams.fromVector([0.5, 2.0, 1.0]) == gp.UnscentedTransformParams(0.5, 2.0, 1.0)
