@@ -411,12 +411,14 @@ int small_tile_threshold() {
 
 int gpk_gemm(gpk_handle h, const GemmDesc& g) {
     if (g.R <= 0 || g.S <= 0 || g.batch <= 0) return GPK_OK;
-    if (g.R % 128 || g.S % 128 || g.K % TK || (g.ldp & 1) || (g.ldq & 1) || (g.ldd & 1) ||
+    // (64-granular shapes are served by the 64 x 64 tile configuration only)
+    const bool small_only = (g.R % 128) || (g.S % 128);
+    if (g.R % 64 || g.S % 64 || g.K % TK || (g.ldp & 1) || (g.ldq & 1) || (g.ldd & 1) ||
         ((uintptr_t)g.P & 15) || ((uintptr_t)g.Q & 15) || ((uintptr_t)g.D & 15) || (g.Cin && (((uintptr_t)g.Cin & 15) || (g.ldc & 1))))
         return gpk_set_error(h, GPK_EINVAL, "gpk_gemm: unaligned problem R=%d S=%d K=%d", g.R, g.S, g.K);
     int64_t tiles = (int64_t)(g.R / 128) * (g.S / 128) * g.batch;
     if (g.tri_out) tiles = (tiles + g.batch * (g.R / 128)) / 2;
-    if (tiles < small_tile_threshold()) {
+    if (small_only || tiles < small_tile_threshold()) {
         const int sk = try_stream_k(h, g);
         if (sk != 0) return sk < 0 ? sk : GPK_OK;
         return dispatch<SmallTile>(h, g, 1);

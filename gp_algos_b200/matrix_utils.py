@@ -57,9 +57,14 @@ def buildKernelDerMatrix(kernelFun, data, paramNum: int, handle=None) -> np.ndar
 
 def _solve(upper, T, b, transposed, handle):
     h = handle or _lib.default_handle()
-    T = _lib.fmat(T)
+    T = np.asarray(T, dtype=np.float64)
     if T.ndim != 2 or T.shape[0] != T.shape[1]:
         raise _lib.IllegalArgumentError(_lib.GPK_EINVAL, "requirement failed")  # MatrixUtils.scala:125
+    if T.flags.c_contiguous and not T.flags.f_contiguous:
+        # a row-major operand IS the column-major storage of its transpose: hand the buffer over as it lies and flip the
+        # view flag instead of re-striding n^2 doubles on the host (the effective operand, hence `upper`, is unchanged)
+        T, transposed = T.T, not transposed
+    T = _lib.fmat(T)
     n = T.shape[0]
     b = _lib.fmat(b)
     vec = b.ndim == 1

@@ -136,6 +136,10 @@ def test_triangular_solves_match_oracle(n, m):
     U = np.ascontiguousarray(L.T)
     assert np.allclose(MU.backSolve(U, B), sla.solve_triangular(U, B, lower=False), rtol=1e-9, atol=1e-12)
     assert np.allclose(MU.forwardSolve(U, b, transposed=True), sla.solve_triangular(L, b, lower=True), rtol=1e-9, atol=1e-12)
+    # a row-major operand is passed as the column-major storage of its transpose (no host re-striding): same bits either way
+    Lf, Lc = np.asfortranarray(L), np.ascontiguousarray(L)
+    assert np.array_equal(MU.forwardSolve(Lf, B), MU.forwardSolve(Lc, B))
+    assert np.array_equal(MU.backSolve(Lf, b, transposed=True), MU.backSolve(Lc, b, transposed=True))
 
 
 @pytest.mark.parametrize("n", [4, 128, 200, 515])
