@@ -469,7 +469,7 @@ int stage_panel(gpk_handle h, double* A, double* Li, int N, int bk, int sk, int 
 }
 
 int potrf_factor_pipelined(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev, double* rhsB, double* rhsV,
-                           int rhsM) {
+                           int rhsM, const GpkRowsHook* on_rows = nullptr) {
     const int nbk = potrf_nb(N);
     const int nt = (N + nbk - 1) / nbk;
     auto bs = [&](int k) { return k * nbk < N ? k * nbk : N; };
@@ -552,6 +552,12 @@ int potrf_factor_pipelined(gpk_handle h, double* A, double* Li, double* T, int N
             g.D = rhsV + bk; g.ldd = N; g.R = rhsM; g.S = sk; g.K = sk; g.ke_s = 1; g.heavy_last = 1;
             rc = gpk_gemm(h, g);
             if (rc) return rc;
+            if (on_rows) {                                   // rows [bk, bk + sk) of V are final: the caller's consumer may start
+                cudaEvent_t evV = next_event(h);
+                GPK_CUDA(h, cudaEventRecord(evV, R));
+                rc = (*on_rows)(bk, sk, evV);
+                if (rc) return rc;
+            }
             if (k + 1 < nt) {
                 const int b1 = bs(k + 1);
                 GPK_CUDA(h, cudaStreamWaitEvent(R, evPc, 0));
@@ -594,16 +600,21 @@ int gpk_potrf_factor(gpk_handle h, double* A, double* Li, double* T, int N, int*
 // destroyed.  EP's posterior re-factorisation (EpParameterEstimator.scala:58-59: cholesky, then forwardSolve with n right-hand
 // sides) is this call.  Large N: the look-ahead driver with the right-hand sides riding along (no L^-1 is ever formed:
 // n^3/3 + n^2 M flops); small N: L^-1 by the recursion and one GEMM.
-int gpk_potrf_factor_solve(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev, double* B, double* V, int M) {
+int gpk_potrf_factor_solve(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev, double* B, double* V, int M,
+                           const GpkRowsHook* on_rows) {
     if (N >= 2 * potrf_nb(N))
-        return potrf_factor_pipelined(h, A, Li, T, N, info_dev, B, V, M);
+        return potrf_factor_pipelined(h, A, Li, T, N, info_dev, B, V, M, on_rows);
     int rc = gpk_potrf_inv(h, A, Li, T, N, 1, info_dev, 1);
     if (rc) return rc;
     GemmDesc g = gemm_desc();                                       // V = L^-1 B: C(m,c) = sum_{k<=m} Li(m,k) B(k,c)
     g.P = B; g.ldp = N; g.p_kcontig = 1;
     g.Q = Li; g.ldq = N; g.q_kcontig = 0;
     g.D = V; g.ldd = N; g.R = M; g.S = N; g.K = N; g.ke_s = 1; g.heavy_last = 1;
-    return gpk_gemm(h, g);
+    rc = gpk_gemm(h, g);
+    if (rc || !on_rows) return rc;
+    cudaEvent_t evV = next_event(h);                                // all rows at once
+    GPK_CUDA(h, cudaEventRecord(evV, h->stream));
+    return (*on_rows)(0, N, evV);
 }
 
 bool gpk_use_pipelined(int N, int batch) { return batch == 1 && pipe_min() > 0 && N >= pipe_min() && N >= 2 * pipe_nb(); }

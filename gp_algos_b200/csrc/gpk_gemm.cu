@@ -418,6 +418,9 @@ int gpk_gemm(gpk_handle h, const GemmDesc& g) {
         return gpk_set_error(h, GPK_EINVAL, "gpk_gemm: unaligned problem R=%d S=%d K=%d", g.R, g.S, g.K);
     int64_t tiles = (int64_t)(g.R / 128) * (g.S / 128) * g.batch;
     if (g.tri_out) tiles = (tiles + g.batch * (g.R / 128)) / 2;
+    if (g.cfg_hint == 1 && !small_only) return dispatch<BigTile>(h, g, 0);
+    if (g.cfg_hint == 2 && !small_only) return dispatch<WideTile>(h, g, 2);
+    if (g.cfg_hint == 3 && g.R % 128 == 0) return dispatch<MidTile>(h, g, 3);
     if (small_only || tiles < small_tile_threshold()) {
         const int sk = try_stream_k(h, g);
         if (sk != 0) return sk < 0 ? sk : GPK_OK;

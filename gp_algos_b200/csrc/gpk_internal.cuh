@@ -115,6 +115,7 @@ struct GemmDesc {
     int tri_out;
     int kb_r, kb_s, ke_r, ke_s;
     int heavy_last;  // reverse tile order (heavy tiles are at high indices)
+    int cfg_hint;    // 0: default tile configuration; 1 / 2 / 3: 128x128 on 8 warps / 128x128 on 16 warps / 128x64, when the shape allows
 };
 static inline GemmDesc gemm_desc() {
     GemmDesc g;
@@ -241,7 +242,11 @@ int gpk_potrf_inv_pipelined(gpk_handle h, double* A, double* Li, double* Kinv, d
                             cudaEvent_t* kinv_done = nullptr, int factor_only = 0, double* rhsB = nullptr, double* rhsV = nullptr,
                             int rhsM = 0);
 // A -> L in place and V = L^-1 B (B, V: N x M, ld N; B destroyed); Li: N x N staging (holds L^-1 only when N is small)
-int gpk_potrf_factor_solve(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev, double* B, double* V, int M);
+// on_rows (optional): called on the host, in order, once per block row of V -- rows [row0, row0 + rows) are final when `ready` fires
+// (the event is recorded on one of the handle's internal streams); lets a consumer of V start before the factorisation is done.
+typedef std::function<int(int row0, int rows, cudaEvent_t ready)> GpkRowsHook;
+int gpk_potrf_factor_solve(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev, double* B, double* V, int M,
+                           const GpkRowsHook* on_rows = nullptr);
 // L only (plus the inverses of the diagonal blocks, left in Li's diagonal blocks): n^3/3 flops.  Li: N x N staging.
 int gpk_potrf_factor(gpk_handle h, double* A, double* Li, double* T, int N, int* info_dev);
 // X = Lw^-1 B (backward == 0) or Lw^-t B (backward != 0) by blocked substitution on the padded lower factor Lw (N x N, ld N).

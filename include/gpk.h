@@ -55,7 +55,7 @@ const char* gpk_version(void);
  * serial spine of every factorisation) once on a synthetic SPD block and returns 17 clock64() stamps, one per phase
  * (tools/base_timing.py prints them; profiles/r02_base_timing.log). */
 int gpk_debug_base_timing(gpk_handle h, long long* stamps_host);
-int gpk_debug_ep_site_timing(gpk_handle h, int chain, long long* stamps_host);   /* 5 x 64 clock64() stamps of the EP site kernel */
+int gpk_debug_ep_site_timing(gpk_handle h, int chain, long long* stamps_host);   /* 5 x 64 clock64() stamps of the EP site kernel + [320]: ns of one unstamped launch */
 /* Launch sequences that callers repeat verbatim are captured into CUDA graphs and replayed: the single-problem
  * gpk_gp_nll_grad[_dev] evaluation (an optimiser's objective, GpPredictor.scala:126-142; same buffers and shape, new
  * hyper-parameters through device memory) from its second call on, and the EP sweep (EpParameterEstimator.scala:37-67) once

@@ -5,10 +5,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from gp_algos_b200 import _lib
 h = _lib.default_handle()
-st = (C.c_longlong * 320)()
+st = (C.c_longlong * 321)()
 for chain in (1, 2, 3, 4, 10):     # 10 = warp-specialised kernel (ep_sites_block_p, branch-free scalar update): loop-top stamps only
     h.check(h.lib.gpk_debug_ep_site_timing(h.h, chain, C.addressof(st)))
-    v = np.array(list(st), dtype=np.int64).reshape(64, 5)
+    v = np.array(list(st)[:320], dtype=np.int64).reshape(64, 5)
     top, sc, dn, pub, bar = v.T
     per_site = np.diff(top)
     print(f"chain {chain}: cycles per site  median {np.median(per_site):.0f}  (k=1..8 {per_site[:8].tolist()}, k=56..63 {per_site[-8:].tolist()})")
@@ -24,3 +24,4 @@ for chain in (1, 2, 3, 4, 10):     # 10 = warp-specialised kernel (ep_sites_bloc
     print(f"   mu / A row / publish median {np.median(pub - dn):.0f}")
     print(f"   barrier              median {np.median(bar - pub):.0f}   (late sites, helper-bound? k=60: {int((bar - pub)[60])})")
     print(f"   barrier -> next top  median {np.median(top[1:] - bar[:-1]):.0f}")
+print(f"unstamped default kernel (ep_sites_block_p), one 64-site block, CUDA events: {st[320] / 1e3:.1f} us")
