@@ -108,6 +108,7 @@ def load():
         lib.gpk_gp_predict_batched.argtypes = [vp, ci, vp, ci, ci, _i64, _i64, vp, vp, vp, ci, _i64, _i64, ci, cd, vp, vp, vp, vp]
         lib.gpk_debug_base_timing.argtypes = [vp, vp]
         lib.gpk_debug_ep_site_timing.argtypes = [vp, C.c_int, vp]
+        lib.gpk_debug_partition.argtypes = [vp, vp, vp]
         lib.gpk_mg_create.argtypes = [C.POINTER(vp), ci, vp]
         lib.gpk_mg_destroy.argtypes = [vp]
         lib.gpk_mg_last_error.argtypes = [vp]

@@ -24,6 +24,8 @@ struct gpk_handle_s {
     cudaStream_t side[GPK_NSIDE];
     cudaStream_t grp[GPK_NGROUP - 1];   // same priority as the main stream
     cudaStream_t pipe[GPK_NPIPE];   // lowest-priority streams of the pipelined factorisation (trailing updates; inverse rows; K^-1)
+    cudaStream_t mid;               // one level above pipe[]: the trailing update when consumers of the factor ride along on pipe[]
+    int prio_mid;
     cudaEvent_t evpool[GPK_NEVENTS];
     unsigned ev_next;
     // grow-only device arenas (A: factor / K^-1, B: L^-1, T: GEMM scratch, misc: small vectors)
@@ -45,9 +47,18 @@ struct gpk_handle_s {
     struct gpk_graph_slot* slots[2];   // cached graphs (gpk_graph.cu): GPK_SLOT_EVAL, GPK_SLOT_EP_SWEEP
     struct gpk_capture_log* cap;  // non-null while capturing: every kernel node with the priority of the stream it came from
     int prio_main, prio_side, prio_pipe;
+    struct gpk_partition* part;   // SM partition for the spine of the look-ahead factorisation (gpk_part.cu), created on first use
+    int part_state;               // 0 not tried, 1 ready, -1 unavailable / off
     int kernel_family;            // gpk_kernel_family: how (D, theta) arguments are interpreted
     char err[512];
 };
+// ---- SM partition (gpk_part.cu) ----
+int gpk_partition_get(gpk_handle h, struct gpk_partition** out);      // 1 when available
+void gpk_partition_destroy(struct gpk_partition* p);
+int gpk_partition_sms(const struct gpk_partition* p, int which);      // 0 spine, 1 bulk
+cudaStream_t gpk_partition_stream(const struct gpk_partition* p, int kind, int i);   // 0 spine, 1 spine side i, 2 bulk near-critical, 3 bulk i
+// does the factor-only look-ahead driver run partitioned for this size?  (not while a graph is being captured)
+bool gpk_partition_active(gpk_handle h, int N, struct gpk_partition** out);
 // ---- graph replay (gpk_graph.cu) ----
 #define GPK_NSLOTS 2
 enum { GPK_SLOT_EVAL = 0, GPK_SLOT_EP_SWEEP = 1 };

@@ -56,6 +56,10 @@ const char* gpk_version(void);
  * (tools/base_timing.py prints them; profiles/r02_base_timing.log). */
 int gpk_debug_base_timing(gpk_handle h, long long* stamps_host);
 int gpk_debug_ep_site_timing(gpk_handle h, int chain, long long* stamps_host);   /* 5 x 64 clock64() stamps of the EP site kernel + [320]: ns of one unstamped launch */
+/* Opt-in SM partition for the spine of the factor-only look-ahead driver (GPK_PARTITION=1, GPK_SPINE_SMS; CUDA green contexts):
+ * returns 1 and the two SM counts when the partition is up on this handle (creating it on first use), 0 when it is off or the
+ * driver / device does not support it.  Measured and left off by default. */
+int gpk_debug_partition(gpk_handle h, int* spine_sms, int* bulk_sms);
 /* Launch sequences that callers repeat verbatim are captured into CUDA graphs and replayed: the single-problem
  * gpk_gp_nll_grad[_dev] evaluation (an optimiser's objective, GpPredictor.scala:126-142; same buffers and shape, new
  * hyper-parameters through device memory) from its second call on, and the EP sweep (EpParameterEstimator.scala:37-67) once
