@@ -38,7 +38,7 @@ def test_golden_c3_small():
     assert close(p, g["prob"]) and close(clf.fMean, g["fmean"]) and close(clf.fVariance, g["fvar"])
 
 
-@pytest.mark.parametrize("n,D,sweeps", [(50, 2, 2), (130, 3, 3), (300, 4, 2)])
+@pytest.mark.parametrize("n,D,sweeps", [(50, 2, 2), (65, 2, 3), (130, 3, 3), (300, 4, 2)])   # 65, 130: a last block of 1 / 2 sites
 def test_ep_vs_literal_oracle(n, D, sweeps):
     X, t, th = orc.make_c3(n=n, D=D, seed=n)
     K = orc.lit_build_kernel_matrix(X, th)
