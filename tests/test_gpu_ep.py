@@ -56,15 +56,16 @@ def test_ep_vs_literal_oracle(n, D, sweeps):
 @pytest.mark.parametrize("n,signal", [(300, 1.0), (1000, 1.0), (200, 40.0)])
 def test_site_kernel_variants_agree(n, signal, monkeypatch):
     """GPK_EP_SITES=5 (warp-specialised kernel, branch-free scalar update with the erfcx table) against =4 (libdevice erfc / exp
-    chain), and the three flush schedules (per block, cross first, pairs): same site parameters to rounding.  n = 300 ends
+    chain), the three flush schedules (per block, cross first, pairs) and the folded apply step: same site parameters to rounding.  n = 300 ends
     in a ragged block (44 sites); signal = 40 drives |z| past 11.3, the table's libdevice fallback."""
     X, t, th = orc.make_c3(n=n, D=3, seed=n + 7)
     th = th.copy(); th[0] = signal
     K = orc.fast_build_kernel_matrix(X, th)
     res = {}
     for name, env in (("w", {"GPK_EP_SITES": "4", "GPK_EP_LOOKAHEAD": "1"}), ("p", {"GPK_EP_SITES": "5", "GPK_EP_LOOKAHEAD": "1"}),
-                      ("p_plain", {"GPK_EP_SITES": "5", "GPK_EP_LOOKAHEAD": "0"}), ("p_pairs", {"GPK_EP_SITES": "5", "GPK_EP_LOOKAHEAD": "2"})):
-        for k in ("GPK_EP_SITES", "GPK_EP_LOOKAHEAD"):
+                      ("p_plain", {"GPK_EP_SITES": "5", "GPK_EP_LOOKAHEAD": "0"}), ("p_pairs", {"GPK_EP_SITES": "5", "GPK_EP_LOOKAHEAD": "2"}),
+                      ("p_pairs_folded", {"GPK_EP_SITES": "5", "GPK_EP_LOOKAHEAD": "2", "GPK_EP_FOLD": "1"})):
+        for k in ("GPK_EP_SITES", "GPK_EP_LOOKAHEAD", "GPK_EP_FOLD"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -72,6 +73,8 @@ def test_site_kernel_variants_agree(n, signal, monkeypatch):
         res[name] = (site.tauSiteParams, site.niSiteParams, site.marginalLogLikelihood)
     o = orc.fast_ep_estimate(K, t, fixed_sweeps=3)
     assert np.all(np.isfinite(o["tau"])) and np.all(np.isfinite(res["p"][0]))
+    # the folded schedule moves one block row of the apply step into the site kernel, same arithmetic in the same order
+    assert np.array_equal(res["p_pairs"][0], res["p_pairs_folded"][0]) and np.array_equal(res["p_pairs"][1], res["p_pairs_folded"][1])
     for name in ("p", "p_plain", "p_pairs"):
         assert close(res[name][0], res["w"][0], 1e-11) and close(res[name][1], res["w"][1], 1e-11)
         assert abs(res[name][2] - res["w"][2]) <= 1e-11 * abs(res["w"][2])
