@@ -428,17 +428,29 @@ int gpk_potrf_lower_dev(gpk_handle h, double* dA, int n, int64_t lda, int* info_
     ARENA_OR_FAIL(dLi, double*, h, ARENA_B, (size_t)N * N * sizeof(double));
     ARENA_OR_FAIL(dT, double*, h, ARENA_T, gpk_chol_scratch_doubles(N) * sizeof(double));
     int* info = info_dev ? info_dev : h->d_info;
-    if (N == n && lda == n && !((uintptr_t)dA & 15)) {
-        int rc = gpk_potrf_factor(h, dA, dLi, dT, N, info);
-        if (rc) return rc;
-        return gpk_store_lower(h, dA, n, dA, N, n);     // zero the strict upper triangle (element-wise, in place)
+    const bool in_place = N == n && lda == n && !((uintptr_t)dA & 15);
+    double* dW = dA;
+    if (!in_place) {
+        dW = (double*)gpk_arena(h, ARENA_A, (size_t)N * N * sizeof(double));
+        if (!dW) return gpk_set_error(h, GPK_ENOMEM, "device allocation failed");
     }
-    ARENA_OR_FAIL(dW, double*, h, ARENA_A, (size_t)N * N * sizeof(double));
-    int rc = gpk_load_sym_padded(h, dW, N, dA, n, lda, nullptr);
-    if (rc) return rc;
-    rc = gpk_potrf_factor(h, dW, dLi, dT, N, info);
-    if (rc) return rc;
-    return gpk_store_lower(h, dA, lda, dW, N, n);
+    // ~40 launches per block column, most of them small and dependent: a caller that factors the same buffer again (a solver in a
+    // loop) replays the launch sequence from a graph, like the evaluation and the EP sweep -- up to N = 4096, where the launch gaps
+    // dominate (2.74 -> 2.45 ms at n = 4096; at n = 8192 replay is SLOWER, 8.77 -> 9.27 ms: profiles/r02_potrf_nb.log)
+    auto body = [&]() {
+        int rc = GPK_OK;
+        if (!in_place) rc = gpk_load_sym_padded(h, dW, N, dA, n, lda, nullptr);
+        if (!rc) rc = gpk_potrf_factor(h, dW, dLi, dT, N, info);
+        if (!rc) rc = in_place ? gpk_store_lower(h, dA, n, dA, N, n)     // zero the strict upper triangle (element-wise, in place)
+                               : gpk_store_lower(h, dA, lda, dW, N, n);
+        return rc;
+    };
+    if (!h->graph_mode || N < 1024 || N > 4096) return body();
+    GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.p[0] = dA; key.p[1] = dW; key.p[2] = dLi; key.p[3] = dT; key.p[4] = info;
+    key.i[0] = n; key.i[1] = N; key.i[2] = lda;
+    return gpk_graph_run(h, GPK_SLOT_POTRF, key, 1, body, "Cholesky factorisation");
 }
 
 int gpk_syrk_lower_dev(gpk_handle h, const double* dP, int64_t ldp, double* dC, int64_t ldc, int n, int k) {

@@ -44,7 +44,7 @@ struct gpk_handle_s {
     // optimiser calls it over and over with the same buffers and new hyper-parameters)
     int graph_mode;               // 0 off, 1 capture on the second call with one signature and replay from then on
     unsigned arena_epoch;         // bumped whenever an arena is (re)allocated: a cached graph holds arena pointers
-    struct gpk_graph_slot* slots[2];   // cached graphs (gpk_graph.cu): GPK_SLOT_EVAL, GPK_SLOT_EP_SWEEP
+    struct gpk_graph_slot* slots[3];   // cached graphs (gpk_graph.cu): GPK_SLOT_EVAL, GPK_SLOT_EP_SWEEP, GPK_SLOT_POTRF
     struct gpk_capture_log* cap;  // non-null while capturing: every kernel node with the priority of the stream it came from
     int prio_main, prio_side, prio_pipe;
     struct gpk_partition* part;   // SM partition for the spine of the look-ahead factorisation (gpk_part.cu), created on first use
@@ -60,8 +60,8 @@ cudaStream_t gpk_partition_stream(const struct gpk_partition* p, int kind, int i
 // does the factor-only look-ahead driver run partitioned for this size?  (not while a graph is being captured)
 bool gpk_partition_active(gpk_handle h, int N, struct gpk_partition** out);
 // ---- graph replay (gpk_graph.cu) ----
-#define GPK_NSLOTS 2
-enum { GPK_SLOT_EVAL = 0, GPK_SLOT_EP_SWEEP = 1 };
+#define GPK_NSLOTS 3
+enum { GPK_SLOT_EVAL = 0, GPK_SLOT_EP_SWEEP = 1, GPK_SLOT_POTRF = 2 };
 struct GraphKey { const void* p[6]; int64_t i[6]; };   // zero-initialise, then fill: compared bytewise
 void gpk_capture_note(gpk_handle h);
 void gpk_graph_drop_all(gpk_handle h);                  // forget every cached graph (handle teardown, graph mode off)
