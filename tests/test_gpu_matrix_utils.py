@@ -223,3 +223,35 @@ def test_cholesky_on_the_sm_partition(monkeypatch):
     L2 = MU.cholesky(K, handle=h)
     assert np.array_equal(L1, L2)
     assert np.allclose(L1, L0, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("n,lda", [(2048, 2048), (1500, 1504)])
+def test_potrf_lower_dev_graph_replay(n, lda):
+    """The same buffers factored again: eager first, captured into a CUDA graph at the second call, replayed afterwards
+    (N <= 4096) -- the three must agree bit for bit, and a not-positive-definite input must still report its leading minor."""
+    import torch
+    from gp_algos_b200 import _lib
+    X, y, th = orc.make_c2(n=n, D=8, seed=n + 17)
+    K = orc.fast_build_kernel_matrix(X, th)
+    buf = np.zeros((n, lda)); buf[:, :n] = K.T
+    src = torch.from_numpy(buf.reshape(-1).copy()).cuda()
+    d = torch.empty_like(src)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    h = _lib.Handle(0, torch.cuda.current_stream().cuda_stream)
+    outs = []
+    for rep in range(4):
+        d.copy_(src)
+        h.check(h.lib.gpk_potrf_lower_dev(h.h, d.data_ptr(), n, lda, info.data_ptr()))
+        h.synchronize()
+        assert int(info.item()) == 0
+        outs.append(d.cpu().numpy().copy())
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+    L = outs[0].reshape(n, lda)[:, :n].T
+    assert np.linalg.norm(L @ L.T - K) <= 8 * n * np.finfo(float).eps * np.linalg.norm(K)
+    Kb = K.copy(); Kb[n // 3, n // 3] = -1.0
+    buf[:, :n] = Kb.T
+    d.copy_(torch.from_numpy(buf.reshape(-1).copy()).cuda())
+    h.check(h.lib.gpk_potrf_lower_dev(h.h, d.data_ptr(), n, lda, info.data_ptr()))      # replayed graph, other data
+    h.synchronize()
+    assert int(info.item()) == n // 3 + 1
