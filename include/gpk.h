@@ -67,8 +67,9 @@ int gpk_debug_ep_site_timing(gpk_handle h, int chain, long long* stamps_host);
 int gpk_debug_partition(gpk_handle h, int* spine_sms, int* bulk_sms);
 /* Launch sequences that callers repeat verbatim are captured into CUDA graphs and replayed: the single-problem
  * gpk_gp_nll_grad[_dev] evaluation (an optimiser's objective, GpPredictor.scala:126-142; same buffers and shape, new
- * hyper-parameters through device memory) from its second call on, and the EP sweep (EpParameterEstimator.scala:37-67) once
- * ~30 sweeps of one size have run on the handle (capturing costs about one sweep).  on = 0: eager launches only; 1 (default,
+ * hyper-parameters through device memory) from its second call on, the device-resident factor-only Cholesky up to n = 4096
+ * when the same buffers are factored again, and -- only with GPK_GRAPH_AFTER_EP=k in the environment, after k eager sweeps of one
+ * size -- the EP sweep (EpParameterEstimator.scala:37-67; measured slower than eager launches since the round-2 rework).  on = 0: eager launches only; 1 (default,
  * or the GPK_GRAPH environment variable): as described; 2: capture at the first repetition of anything.  Results are
  * bit-identical in every mode. */
 int gpk_set_graph_mode(gpk_handle h, int on);
