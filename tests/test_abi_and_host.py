@@ -204,3 +204,25 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     rc, version = out.stdout.split(" ", 1)
     assert "sm_100a" in version
     assert int(rc) == (0 if _have_gpu() else _lib.GPK_ECUDA)
+
+
+def test_erfcx_table_matches_its_generator():
+    """gp_algos_b200/csrc/gpk_erfcx_table.inc (the EP site kernel's phi/Phi table) is what tools/make_erfcx_table.py generates,
+    and the table is as accurate as the kernel's header says (erfcx 4.4e-16, phi/Phi 1.8e-14 relative)."""
+    mp = pytest.importorskip("mpmath")
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_erfcx_table", os.path.join(root, "tools", "make_erfcx_table.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    rows = [l for l in open(os.path.join(root, "gp_algos_b200", "csrc", "gpk_erfcx_table.inc")) if l.startswith("{")]
+    assert len(rows) == gen.NI
+    T = np.array([[float.fromhex(v) for v in r.strip().strip("{},").split(", ")] for r in rows])
+    assert T.shape == (gen.NI, gen.DEG + 1)
+    for i in (0, 7, 31, 63):
+        assert np.array_equal(T[i], np.array(gen.fit(i)))
+    xs = np.linspace(0, 8, 801)[:-1]
+    ref = np.array([float(gen.erfcx(mp.mpf(float(x)))) for x in xs])
+    assert np.max(np.abs(gen.table_erfcx(T, xs) / ref - 1)) < 6e-16
+    zs = np.linspace(-11.3, 11.3, 453)
+    rr = np.array([float(mp.npdf(mp.mpf(float(z))) / mp.ncdf(mp.mpf(float(z)))) for z in zs])
+    assert np.max(np.abs(gen.ratio(T, zs) / rr - 1)) < 3e-14
