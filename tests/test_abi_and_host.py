@@ -226,3 +226,48 @@ def test_erfcx_table_matches_its_generator():
     zs = np.linspace(-11.3, 11.3, 453)
     rr = np.array([float(mp.npdf(mp.mpf(float(z))) / mp.ncdf(mp.mpf(float(z)))) for z in zs])
     assert np.max(np.abs(gen.ratio(T, zs) / rr - 1)) < 3e-14
+
+
+def test_ep_fast_site_update_algebra_matches_the_reference_formulas():
+    """The EP site kernel's scalar update (gpk_ep.cu: ep_site_fast -- cavity through 1 - tau_i Sigma_ii, phi/Phi through the erfcx
+    table, c and g without 1/sig_hat on the chain) restated in NumPy against the formulas as written in
+    EpParameterEstimator.scala:41-55, over the ranges an EP run visits."""
+    mp = pytest.importorskip("mpmath")
+    import importlib.util, os
+    from scipy.stats import norm
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_erfcx_table", os.path.join(root, "tools", "make_erfcx_table.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    rows = [l for l in open(os.path.join(root, "gp_algos_b200", "csrc", "gpk_erfcx_table.inc")) if l.startswith("{")]
+    T = np.array([[float.fromhex(v) for v in r.strip().strip("{},").split(", ")] for r in rows])
+    rng = np.random.default_rng(7)
+    m = 20000
+    sii = rng.uniform(0.02, 3.0, m); t_old = rng.uniform(0.0, 0.3, m) / sii; mui = rng.normal(0, 2, m)
+    n_old = rng.normal(0, 1, m) * t_old; y = rng.choice([-1.0, 1.0], m)
+    # the reference, as written
+    ct = 1 / sii - t_old; cn = mui / sii - n_old
+    csig = 1 / ct; cmu = cn * csig
+    z = y * cmu / np.sqrt(1 + csig)
+    ok = np.abs(z) < 11.0                                    # (beyond: the kernel's libdevice fallback)
+    ratio = norm.pdf(z) / norm.cdf(z)
+    mu_hat = cmu + y * csig * ratio / np.sqrt(1 + csig)
+    sig_hat = csig - csig ** 2 * ratio / (1 + csig) * (z + ratio)
+    dtau = 1 / sig_hat - ct - t_old; n_new = mu_hat / sig_hat - cn
+    c = dtau / (1 + dtau * sii); dnu = n_new - n_old; g = dnu - c * (mui + dnu * sii)
+    # the kernel's formulation
+    den = 1 - t_old * sii; num = mui - n_old * sii
+    r = 1 / den; rs = 1 / sii; rt = np.sqrt(den) / np.sqrt(den + sii)
+    csig2 = sii * r; cmu2 = num * r; ct2 = den * rs; cn2 = num * rs
+    z2 = (y * cmu2) * rt
+    ratio2 = gen.ratio(T, z2)
+    mu_hat2 = cmu2 + (y * csig2 * rt) * ratio2
+    sig_hat2 = csig2 - (csig2 * rt) ** 2 * (ratio2 * (z2 + ratio2))
+    c2 = (sii - sig_hat2) * rs * rs; g2 = (mu_hat2 - mui) * rs
+    dtau2 = 1 / sig_hat2 - rs; n_new2 = mu_hat2 / sig_hat2 - cn2
+
+    def rel(a, b):
+        return np.max(np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-3 * np.abs(b[ok]).max()))
+    assert ok.sum() > 0.95 * m
+    assert rel(ct2, ct) < 1e-12 and rel(cn2, cn) < 1e-12
+    assert rel(dtau2, dtau) < 1e-10 and rel(n_new2, n_new) < 1e-10      # (1/sig_hat - 1/sii: a difference of close numbers)
+    assert rel(c2, c) < 1e-10 and rel(g2, g) < 1e-10
