@@ -271,3 +271,39 @@ def test_ep_fast_site_update_algebra_matches_the_reference_formulas():
     assert rel(ct2, ct) < 1e-12 and rel(cn2, cn) < 1e-12
     assert rel(dtau2, dtau) < 1e-10 and rel(n_new2, n_new) < 1e-10      # (1/sig_hat - 1/sii: a difference of close numbers)
     assert rel(c2, c) < 1e-10 and rel(g2, g) < 1e-10
+
+
+def test_triangular_solve_host_logic_passes_row_major_operands_without_copy():
+    """MatrixUtils.forwardSolve / backSolve (utils/MatrixUtils.scala:17-35): a row-major triangular operand IS the column-major
+    storage of its transpose, so the host mirror hands the caller's buffer to gpk_trsm as it lies and flips the view flag;
+    a column-major operand goes through unchanged; `upper` (the EFFECTIVE operand's shape) never changes."""
+    from gp_algos_b200 import matrix_utils as MU
+    calls = []
+
+    class FakeLib:
+        def gpk_trsm(self, h, upper, transposed, T, n, ldt, B, nrhs, ldb, X, ldx):
+            calls.append((upper, transposed, T.value, n, ldt, nrhs))
+            return 0
+
+    class FakeHandle:
+        h = None
+        lib = FakeLib()
+
+        def check(self, status):
+            assert status == 0
+
+    n = 7
+    Lc = np.ascontiguousarray(np.tril(np.arange(1.0, n * n + 1).reshape(n, n)))      # row-major
+    Lf = np.asfortranarray(Lc)                                                         # column-major
+    b = np.ones(n)
+    MU.forwardSolve(Lc, b, handle=FakeHandle())
+    MU.forwardSolve(Lf, b, handle=FakeHandle())
+    MU.backSolve(Lc, b, transposed=True, handle=FakeHandle())
+    MU.backSolve(Lf, b, transposed=True, handle=FakeHandle())
+    (u0, t0, p0, *_), (u1, t1, p1, *_), (u2, t2, p2, *_), (u3, t3, p3, *_) = calls
+    assert (u0, t0) == (0, 1) and p0 == Lc.ctypes.data          # caller's row-major buffer, no copy, flag flipped
+    assert (u1, t1) == (0, 0) and p1 == Lf.ctypes.data          # caller's column-major buffer, unchanged
+    assert (u2, t2) == (1, 0) and p2 == Lc.ctypes.data
+    assert (u3, t3) == (1, 1) and p3 == Lf.ctypes.data
+    with pytest.raises(_lib.IllegalArgumentError):
+        MU.forwardSolve(np.ones((3, 4)), np.ones(3), handle=FakeHandle())              # require(...) at MatrixUtils.scala:125
